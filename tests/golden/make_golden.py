@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz by running the IMPORTED reference code on seeded inputs.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):      python tests/golden/make_golden.py
+
+The reference ships no golden vectors; these fixtures are the pin
+for oracle/cirtorch_oracle.py and, through it, for the CUDA path.  Sizes are small so the
+fixtures stay a few hundred KB.  Where the reference inlines a step in a driver script
+(ranking, mining) the generator executes the same statements, quoted with file:line.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    # inplace_abn (3rd-party CUDA ext, absent here) is only used for an isinstance check
+    stub = types.ModuleType("inplace_abn")
+
+    class _ABN(torch.nn.Module):
+        pass
+
+    stub.ABN = stub.InPlaceABN = stub.InPlaceABNSync = _ABN
+    stub.active_group = stub.set_active_group = lambda *a, **k: None
+    sys.modules["inplace_abn"] = stub
+
+
+def tail_fixtures():
+    from cirtorch.modules.pools import GeM, MAC, SPoC
+    from cirtorch.modules.normalizations import L2N
+    from cirtorch.modules.heads.global_head import globalHead
+
+    g = torch.Generator().manual_seed(1234)
+    cases = {}
+    # (N, C, H, W, p)
+    for name, (n, c, h, w, p) in {
+        "a": (3, 64, 8, 8, 3.0),
+        "b": (2, 48, 7, 5, 2.7),       # HW not a multiple of 4 -> scalar-load path
+        "c": (5, 128, 4, 12, 1.0),
+        "d": (1, 32, 16, 16, 4.5),
+    }.items():
+        x = torch.relu(torch.randn(n, c, h, w, generator=g))
+        x[0, 0] = 0.0                  # an all-zero map row: pure eps clamp
+        head = globalHead(pooling={"name": "GeM", "params": {"p": p, "eps": 1e-6}},
+                          normal={"name": "L2N", "params": {}}, dim=c)
+        torch.manual_seed(7)
+        head.reset_parameters()
+        with torch.no_grad():
+            head.whiten.bias.copy_(0.05 * torch.randn(c, generator=g))
+            cases[f"{name}_x"] = x.numpy()
+            cases[f"{name}_p"] = np.float32(p)
+            cases[f"{name}_W"] = head.whiten.weight.numpy().copy()
+            cases[f"{name}_b"] = head.whiten.bias.numpy().copy()
+            cases[f"{name}_gem"] = GeM(p=p)(x).numpy()
+            cases[f"{name}_l2n"] = L2N()(GeM(p=p)(x)).numpy()
+            cases[f"{name}_mac"] = MAC()(x).numpy()
+            cases[f"{name}_spoc"] = SPoC()(x).numpy()
+            cases[f"{name}_head"] = head(x).contiguous().numpy()
+            cases[f"{name}_head_nowhiten"] = head(x, do_whitening=False).contiguous().numpy()
+    np.savez_compressed(os.path.join(OUT, "tail.npz"), **cases)
+
+
+def whiten_fixtures():
+    from cirtorch.utils.whiten import whitenapply, whitenlearn, pcawhitenlearn, cholesky
+
+    rs = np.random.RandomState(5)
+    D, N = 24, 400
+    basis = rs.randn(D, D)
+    X = basis @ rs.randn(D, N) * np.linspace(2.0, 0.2, D)[:, None]
+    X = (X / np.linalg.norm(X, axis=0, keepdims=True)).astype(np.float32)
+    qidxs = rs.randint(0, N, size=150)
+    pidxs = rs.randint(0, N, size=150)
+    m, P = whitenlearn(X, qidxs, pidxs)
+    mp, Pp = pcawhitenlearn(X)
+    S = np.cov(rs.randn(6, 40))
+    out = dict(X=X, qidxs=qidxs, pidxs=pidxs, m=m, P=P, m_pca=mp, P_pca=Pp,
+               apply=whitenapply(X, m, P), apply_16=whitenapply(X, m, P, dimensions=16),
+               apply_pca=whitenapply(X, mp, Pp), S=S, L=cholesky(S))
+    np.savez_compressed(os.path.join(OUT, "whiten.npz"), **out)
+
+
+def rank_fixtures():
+    rs = np.random.RandomState(11)
+    D, N, Q = 32, 300, 9
+    centres = rs.randn(20, D)
+    V = centres[rs.randint(0, 20, N)] + 0.3 * rs.randn(N, D)
+    Qv = centres[rs.randint(0, 20, Q)] + 0.3 * rs.randn(Q, D)
+    database_vecs = (V / np.linalg.norm(V, axis=1, keepdims=True)).T.astype(np.float32).copy()
+    qvecs = (Qv / np.linalg.norm(Qv, axis=1, keepdims=True)).T.astype(np.float32).copy()
+    # scripts/train_globalF.py:733-734
+    scores = np.dot(database_vecs.T, qvecs)
+    ranks = np.argsort(-scores, axis=0)
+    np.savez_compressed(os.path.join(OUT, "rank.npz"), database_vecs=database_vecs,
+                        qvecs=qvecs, scores=scores, ranks=ranks)
+
+
+def mining_fixtures():
+    g = torch.Generator().manual_seed(21)
+    D, Q, Pn, n_img, n_clu, neg_num = 32, 12, 200, 500, 15, 5
+    clusters = torch.randint(0, n_clu, (n_img,), generator=g).tolist()
+    idxs2images = torch.randperm(n_img, generator=g)[:Pn]
+    query_indices = torch.randperm(n_img, generator=g)[:Q].tolist()
+    centres = torch.randn(n_clu, D, generator=g)
+
+    def vec(i):
+        v = centres[clusters[i]] + 0.5 * torch.randn(D, generator=g)
+        return v / v.norm()
+
+    qvecs = torch.stack([vec(i) for i in query_indices], dim=1)
+    poolvecs = torch.stack([vec(int(i)) for i in idxs2images], dim=1)
+
+    # cirtorch/datasets/globalFeatures/tuples_dataset.py:317-345, executed on CPU tensors
+    scores = torch.mm(poolvecs.t(), qvecs)
+    scores, scores_indices = torch.sort(scores, dim=0, descending=True)
+    average_negative_distance = torch.tensor(0).float()
+    negative_distance = torch.tensor(0).float()
+    negative_indices = []
+    for q in range(len(query_indices)):
+        qcluster = clusters[query_indices[q]]
+        clus = [qcluster]
+        nidxs = []
+        r = 0
+        while len(nidxs) < neg_num:
+            potential = idxs2images[scores_indices[r, q]]
+            if not clusters[potential] in clus:
+                nidxs.append(potential)
+                clus.append(clusters[potential])
+                average_negative_distance += torch.pow(
+                    qvecs[:, q] - poolvecs[:, scores_indices[r, q]] + 1e-6, 2).sum(dim=0).sqrt()
+                negative_distance += 1
+            r += 1
+        negative_indices.append([int(i) for i in nidxs])
+    np.savez_compressed(os.path.join(OUT, "mining.npz"), qvecs=qvecs.numpy(),
+                        poolvecs=poolvecs.numpy(), clusters=np.array(clusters),
+                        idxs2images=idxs2images.numpy(), query_indices=np.array(query_indices),
+                        neg_num=neg_num, negative_indices=np.array(negative_indices),
+                        avg_dist=float(average_negative_distance / negative_distance))
+
+
+def eval_fixtures():
+    from cirtorch.utils.evaluation.ParisOxfordEval import compute_ap, compute_map
+
+    rs = np.random.RandomState(3)
+    N, Q = 120, 6
+    ranks = np.stack([rs.permutation(N) for _ in range(Q)], axis=1)
+    gnd, flat = [], {}
+    for i in range(Q):
+        perm = rs.permutation(N)
+        easy, hard, junk = perm[:5], perm[5:9], perm[9:15]
+        if i == 4:
+            easy = easy[:0]
+            hard = hard[:0]      # query without positives -> skipped
+        gnd.append({"ok": np.concatenate([easy, hard]), "junk": junk})
+        flat[f"ok{i}"] = gnd[-1]["ok"]
+        flat[f"junk{i}"] = junk
+    kappas = [1, 5, 10]
+    mp, aps, pr, prs = compute_map(ranks, gnd, kappas)
+    ap_direct = compute_ap(np.array([0, 3, 4, 10]), 6)
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), ranks=ranks, map=mp, aps=aps, pr=pr,
+                        prs=prs, ap_direct=ap_direct, nq=Q, **flat)
+
+
+def multiscale_fixture():
+    # cirtorch/models/GF_net.py:84-85 on synthetic per-scale predictions
+    g = torch.Generator().manual_seed(9)
+    preds = [torch.nn.functional.normalize(torch.randn(16, 5, generator=g), dim=0) for _ in range(3)]
+    pred = torch.cat([p.unsqueeze(0) for p in preds], dim=0).permute(1, 2, 0)
+    pred = torch.nn.functional.avg_pool1d(pred, kernel_size=3).squeeze(-1)
+    np.savez_compressed(os.path.join(OUT, "multiscale.npz"),
+                        preds=torch.stack(preds).numpy(), out=pred.numpy())
+
+
+if __name__ == "__main__":
+    _import_reference()
+    torch.set_num_threads(1)
+    tail_fixtures()
+    whiten_fixtures()
+    rank_fixtures()
+    mining_fixtures()
+    eval_fixtures()
+    multiscale_fixture()
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
