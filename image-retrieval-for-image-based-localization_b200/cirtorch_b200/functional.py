@@ -1,0 +1,187 @@
+"""Functional form of the fused descriptor tail (the upstream ``cirtorch.layers.functional`` names).
+
+All functions take CUDA fp32 tensors and launch libcir_b200 kernels on the current stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC, CIR_TAIL_NO_WHITEN, CIR_TAIL_POOL_ONLY
+
+_POOL = {"GeM": CIR_POOL_GEM, "GeMmp": CIR_POOL_GEM, "MAC": CIR_POOL_MAC, "SPoC": CIR_POOL_SPOC}
+
+
+def _as_f32_contig(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6):
+    """One cooperative launch of the fused tail.  Returns the physical [N, D] buffer."""
+    _lib.require_cuda(x, p, weight, bias)
+    lib = _lib.load()
+    x = _as_f32_contig(x)
+    if x.dim() != 4:
+        raise ValueError("expected an N x C x H x W feature map, got shape %s" % (tuple(x.shape),))
+    N, Cc, H, W = x.shape
+    whiten = not (flags & (CIR_TAIL_NO_WHITEN | CIR_TAIL_POOL_ONLY))
+    D = weight.shape[0] if whiten else Cc
+    out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+    if N == 0:
+        return out
+    p_stride = 0
+    if p is not None:
+        p = _as_f32_contig(p.detach()).reshape(-1)
+        if p.numel() not in (1, Cc):
+            raise ValueError("GeM exponent must have 1 or C=%d elements, got %d" % (Cc, p.numel()))
+        p_stride = 0 if p.numel() == 1 else 1
+    if whiten:
+        weight = _as_f32_contig(weight.detach())
+        if weight.shape[1] != Cc:
+            raise ValueError("whitening weight is %s, feature map has %d channels" % (tuple(weight.shape), Cc))
+        bias = None if bias is None else _as_f32_contig(bias.detach())
+    import ctypes as C
+    need = C.c_size_t(0)
+    _lib.check(lib.cir_tail_workspace_bytes(N, Cc, D, C.byref(need)), "cir_tail_workspace_bytes")
+    ws = _lib.workspace(x.device, need.value, "tail")
+    rc = lib.cir_tail_fwd(_lib.ptr(x), N, Cc, H, W, _lib.ptr(p), p_stride, float(eps), float(l2_eps), pool_mode,
+                          _lib.ptr(weight) if whiten else None, _lib.ptr(bias) if whiten else None, D,
+                          _lib.ptr(out), D, _lib.ptr(ws), ws.numel(), flags, _lib.stream_of(x))
+    _lib.check(rc, "cir_tail_fwd")
+    return out
+
+
+def _tail_reference_formula(x, p, eps, weight, bias, pooling, flags, l2_eps):
+    """The tail written with stock differentiable torch ops -- used ONLY to obtain gradients
+    (recompute-in-backward); the forward values always come from the CUDA kernel."""
+    if pooling in ("GeM", "GeMmp"):
+        pp = p.reshape(1, -1, 1, 1) if p.numel() > 1 else p
+        v = x.clamp(min=eps).pow(pp).mean(dim=(-2, -1)).pow(1.0 / (p if p.numel() > 1 else p))
+    elif pooling == "MAC":
+        v = x.amax(dim=(-2, -1))
+    else:
+        v = x.mean(dim=(-2, -1))
+    if flags & CIR_TAIL_POOL_ONLY:
+        return v
+    v = v / (v.norm(p=2, dim=1, keepdim=True) + l2_eps)
+    if not (flags & CIR_TAIL_NO_WHITEN):
+        v = torch.nn.functional.linear(v, weight, bias)
+        v = v / (v.norm(p=2, dim=1, keepdim=True) + l2_eps)
+    return v
+
+
+class _TailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, weight, bias, eps, pooling, flags, l2_eps):
+        ctx.cfg = (eps, pooling, flags, l2_eps)
+        ctx.save_for_backward(x, p, weight, bias)
+        return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, p, weight, bias = ctx.saved_tensors
+        eps, pooling, flags, l2_eps = ctx.cfg
+        ins = []
+        with torch.enable_grad():
+            leaves = []
+            for i, t in enumerate((x, p, weight, bias)):
+                if t is None:
+                    leaves.append(None)
+                    continue
+                t2 = t.detach().requires_grad_(ctx.needs_input_grad[i])
+                leaves.append(t2)
+                if ctx.needs_input_grad[i]:
+                    ins.append(t2)
+            y = _tail_reference_formula(leaves[0].float(), leaves[1], eps, leaves[2], leaves[3], pooling, flags, l2_eps)
+            grads = torch.autograd.grad(y, ins, g.contiguous(), allow_unused=True) if ins else ()
+        it = iter(grads)
+        out = [next(it) if (t is not None and ctx.needs_input_grad[i]) else None
+               for i, t in enumerate((x, p, weight, bias))]
+        return (*out, None, None, None, None)
+
+
+def descriptor_tail(x, p=None, eps=1e-6, weight=None, bias=None, pooling="GeM", do_whitening=True,
+                    pool_only=False, l2_eps=1e-6):
+    """pool -> L2N -> (whiten -> L2N).  Returns the physical N x D buffer (row = descriptor).
+
+    globalHead.forward (cirtorch/modules/heads/global_head.py:52-67) returns its transpose view.
+    """
+    if pooling not in _POOL:
+        raise KeyError(pooling)
+    flags = CIR_TAIL_POOL_ONLY if pool_only else (0 if do_whitening else CIR_TAIL_NO_WHITEN)
+    if pooling in ("GeM", "GeMmp"):
+        if p is None:
+            raise ValueError("GeM pooling needs the exponent p")
+        if not torch.is_tensor(p):
+            p = torch.full((1,), float(p), dtype=torch.float32, device=x.device)
+    else:
+        p = None
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and torch.is_tensor(t) and t.requires_grad for t in (x, p, weight, bias))
+    if needs_grad:
+        return _TailFn.apply(x, p, weight if do_whitening and not pool_only else None,
+                             bias if do_whitening and not pool_only else None, eps, pooling, flags, l2_eps)
+    return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
+
+
+def gem(x, p=3, eps=1e-6):
+    """GeM pooling, cirtorch/modules/pools.py:37-38 -> N x C x 1 x 1."""
+    return descriptor_tail(x, p=p, eps=eps, pooling="GeM", pool_only=True)[:, :, None, None]
+
+
+def mac(x):
+    """cirtorch/modules/pools.py:15."""
+    return descriptor_tail(x, pooling="MAC", pool_only=True)[:, :, None, None]
+
+
+def spoc(x):
+    """cirtorch/modules/pools.py:25."""
+    return descriptor_tail(x, pooling="SPoC", pool_only=True)[:, :, None, None]
+
+
+class _L2NFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, eps):
+        ctx.eps = eps
+        ctx.save_for_backward(x2d)
+        return _l2n_rows(x2d, eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        with torch.enable_grad():
+            x2 = x.detach().requires_grad_(True)
+            y = x2 / (x2.norm(p=2, dim=1, keepdim=True) + ctx.eps)
+            (gx,) = torch.autograd.grad(y, x2, g)
+        return gx, None
+
+
+def _l2n_rows(x2d, eps):
+    _lib.require_cuda(x2d)
+    lib = _lib.load()
+    x2d = _as_f32_contig(x2d)
+    out = torch.empty_like(x2d)
+    if x2d.numel():
+        rc = lib.cir_l2n_rows(_lib.ptr(x2d), x2d.shape[0], x2d.shape[1], x2d.shape[1], float(eps),
+                              _lib.ptr(out), x2d.shape[1], _lib.stream_of(x2d))
+        _lib.check(rc, "cir_l2n_rows")
+    return out
+
+
+def l2n(x, eps=1e-6):
+    """x / (||x||_2 over dim 1 + eps), cirtorch/modules/normalizations.py:15-16.  Any rank >= 2."""
+    if x.dim() < 2:
+        raise ValueError("l2n expects at least 2 dimensions")
+    shape = x.shape
+    if x.dim() == 2 or all(s == 1 for s in shape[2:]):
+        x2d = x.reshape(shape[0], shape[1])
+        moved = None
+    else:   # norm over channels at every spatial position: rows = (n, h, w)
+        moved = x.movedim(1, -1)
+        x2d = moved.reshape(-1, shape[1])
+    y = _L2NFn.apply(x2d, eps) if (torch.is_grad_enabled() and x.requires_grad) else _l2n_rows(x2d, eps)
+    if moved is None:
+        return y.reshape(shape)
+    return y.reshape(moved.shape).movedim(-1, 1)

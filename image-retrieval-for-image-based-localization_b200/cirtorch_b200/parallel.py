@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the B200 box,
+gloo in the CPU tests).
+
+Search: the database is sharded by rows, every rank searches its shard with global indices
+(``row_offset``), then ONE all_gather of the per-query top-k lists (scores fp32 + idx int32,
+Q*k*8 bytes per rank) and a k-way merge on every rank.  Exact: top-k(global) == top-k(union of
+shard top-k).  Extraction is data-parallel over contiguous image slices followed by an
+all_gather of the descriptor columns (the reference never gathers -- SURVEY.md quirk Q1).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world_size: int, rank: int):
+    """Contiguous row range [lo, hi) of shard ``rank``."""
+    return (rank * n) // world_size, ((rank + 1) * n) // world_size
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None):
+    """all_gather of per-shard lists [Q, k] -> ([G, Q, k] scores, [G, Q, k] idx), shard order = rank order."""
+    _, ws = world(group)
+    if ws == 1:
+        return scores[None], idx[None]
+    Q = scores.shape[0]
+    s_all = torch.empty((ws * Q,) + tuple(scores.shape[1:]), dtype=scores.dtype, device=scores.device)
+    i_all = torch.empty((ws * Q,) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(s_all, scores.contiguous(), group=group)     # concatenation along dim 0
+    dist.all_gather_into_tensor(i_all, idx.contiguous(), group=group)
+    return s_all.view((ws,) + tuple(scores.shape)), i_all.view((ws,) + tuple(idx.shape))
+
+
+class ShardedIndex:
+    """Row-sharded database: this rank holds rows [lo, hi) of a global N-row database."""
+
+    def __init__(self, local_rows: torch.Tensor, n_global: int, group=None, mode="bf16", keep_fp32=True):
+        from .search import Index
+        self.group = group
+        self.rank, self.world_size = world(group)
+        self.lo, self.hi = shard_bounds(n_global, self.world_size, self.rank)
+        if local_rows.shape[0] != self.hi - self.lo:
+            raise ValueError("rank %d expects %d rows, got %d" % (self.rank, self.hi - self.lo, local_rows.shape[0]))
+        self.n_global = n_global
+        self.index = Index(local_rows, mode=mode, keep_fp32=keep_fp32, row_offset=self.lo)
+
+    def search_local(self, q_rows, k, rescore=None):
+        return self.index.search_rows(q_rows, k, rescore=rescore)
+
+    def search_rows(self, q_rows, k, rescore=None):
+        """Global top-k on every rank: (scores [Q, k], idx [Q, k] global row ids)."""
+        from .search import merge_topk
+        s, i = self.search_local(q_rows, k, rescore=rescore)
+        if self.world_size == 1:
+            return s, i
+        s_all, i_all = gather_topk(s, i, self.group)
+        return merge_topk(s_all, i_all, k)
+
+
+def extract_vectors_dp(net, images, group=None, **kw):
+    """Data-parallel extract_vectors: every rank returns the full D x N matrix (on its device)."""
+    from .extract import extract_vectors
+    rank, ws = world(group)
+    local = extract_vectors(net, images, rank=rank, world_size=ws, **kw)
+    if ws == 1:
+        return local
+    n = len(images)
+    D = local.shape[0]
+    sizes = [shard_bounds(n, ws, r)[1] - shard_bounds(n, ws, r)[0] for r in range(ws)]
+    mx = max(sizes)
+    pad = torch.zeros((mx, D), dtype=local.dtype, device=local.device)
+    pad[:local.shape[1]] = local.t()
+    allv = torch.empty((ws * mx, D), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(allv, pad, group=group)
+    allv = allv.view(ws, mx, D)
+    return torch.cat([allv[r, :sizes[r]] for r in range(ws)], 0).t()

@@ -1,0 +1,299 @@
+// Selection / sorting kernels of the search path.
+//
+//   topk_select_kernel   per query: gather the candidate lists the search kernel produced
+//                        (or G already-sorted top-k lists from G shards / GPUs), bitonic-sort
+//                        them in shared memory in batches of 4096 keys, emit the sorted top-k
+//   rescore_kernel       exact fp32 re-scoring of a candidate list + final ordering
+//   sort_*               full descending argsort of every score row
+//                        (ranks = np.argsort(-scores, axis=0), scripts/train_globalF.py:734)
+//
+// Ordering everywhere: 64-bit keys (ordered score << 32 | ~index), sorted descending ==
+// (score descending, index ascending).  Key 0 = empty slot.
+#include "common.cuh"
+#include "search.cuh"
+
+namespace cir {
+
+constexpr int SEL_N = 4096;
+constexpr int SEL_THREADS = 512;
+
+// in-place descending bitonic sort of buf[0, P) (P a power of two <= SEL_N); `base` is the
+// global position of buf[0] (direction bits above the tile come from it), phases
+// k = kfirst .. klast, strides start at min(k/2, P/2).
+__device__ __forceinline__ void block_bitonic(unsigned long long* buf, int P, long long base, long long kfirst,
+                                              long long klast, int tid, int nthreads) {
+    for (long long k = kfirst; k <= klast; k <<= 1) {
+        int j0 = (k >> 1) < (long long)(P >> 1) ? (int)(k >> 1) : (P >> 1);
+        for (int j = j0; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += nthreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool desc = ((base + i) & k) == 0;
+                const unsigned long long a = buf[i], b = buf[l];
+                if ((a < b) == desc) { buf[i] = b; buf[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct SelParams {
+    // SRC 0: candidate lists of the search kernel
+    const unsigned long long* lists;
+    const int* counts;
+    int Qpad, cap;
+    // SRC 1: G sorted (score, index) lists [G][Q][kin]
+    const float* in_scores;
+    const int32_t* in_idx;
+    int kin;
+    int G, Q, k;
+    float* out_scores;
+    int32_t* out_idx;
+    int out_ld;
+    int32_t idx_offset;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParams p) {
+    __shared__ unsigned long long buf[SEL_N];
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    int fill = 0;
+    int g = 0;
+    while (g < p.G) {
+        while (g < p.G) {
+            const int c = SRC == 0 ? __ldg(p.counts + (size_t)g * p.Qpad + q) : p.kin;
+            if (fill + c > SEL_N) break;
+            if (SRC == 0) {
+                const unsigned long long* L = p.lists + ((size_t)g * p.Qpad + q) * p.cap;
+                for (int t = tid; t < c; t += SEL_THREADS) buf[fill + t] = __ldcg(L + t);
+            } else {
+                const size_t o = ((size_t)g * p.Q + q) * p.kin;
+                for (int t = tid; t < c; t += SEL_THREADS) {
+                    const int32_t ix = __ldg(p.in_idx + o + t);
+                    buf[fill + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+                }
+            }
+            fill += c;
+            ++g;
+        }
+        const int P = next_pow2(fill);
+        for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
+        __syncthreads();
+        block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
+        if (fill > p.k) fill = p.k;
+    }
+    for (int t = tid; t < p.k; t += SEL_THREADS) {
+        const unsigned long long key = t < fill ? buf[t] : 0ull;
+        const bool ok = key != 0ull;
+        p.out_scores[(size_t)q * p.out_ld + t] = ok ? key_score(key) : -INFINITY;
+        p.out_idx[(size_t)q * p.out_ld + t] = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
+    }
+}
+
+int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
+                             float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream) {
+    CIR_REQUIRE(k + cap <= SEL_N, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_N);
+    SelParams p{};
+    p.lists = lists; p.counts = counts; p.Qpad = Qpad; p.cap = cap;
+    p.G = S; p.Q = Q; p.k = k;
+    p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = out_ld; p.idx_offset = idx_offset;
+    topk_select_kernel<0><<<Q, SEL_THREADS, 0, stream>>>(p);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact fp32 re-scoring
+// ---------------------------------------------------------------------------------------
+constexpr int RESCORE_THREADS = 256;
+
+__global__ void __launch_bounds__(RESCORE_THREADS)
+rescore_kernel(const float* __restrict__ q32, const float* __restrict__ db32, long long N, int D,
+               const int32_t* __restrict__ cand, int Kc, int Kp, int32_t idx_offset, float* __restrict__ out_scores,
+               int32_t* __restrict__ out_idx, int k_out) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rs_smem);      // [Kp]
+    float* qv = reinterpret_cast<float*>(rs_smem + (size_t)Kp * 8);                 // [D]
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int d = tid; d < D; d += RESCORE_THREADS) qv[d] = __ldg(q32 + (size_t)q * D + d);
+    for (int t = Kc + tid; t < Kp; t += RESCORE_THREADS) keys[t] = 0ull;
+    __syncthreads();
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(db32) & 15) == 0);
+    for (int c = warp; c < Kc; c += RESCORE_THREADS / 32) {
+        const int32_t ix = __ldg(cand + (size_t)q * Kc + c);
+        const long long row = (long long)ix - idx_offset;
+        unsigned long long key = 0ull;
+        if (ix >= 0 && row >= 0 && row < N) {
+            const float* v = db32 + (size_t)row * D;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (vec) {
+                for (int d = lane * 4; d < D; d += 128) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(v + d));
+                    const float4 y = *reinterpret_cast<const float4*>(qv + d);
+                    a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
+                    a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+                }
+            } else {
+                for (int d = lane; d < D; d += 32) a0 = fmaf(__ldg(v + d), qv[d], a0);
+            }
+            const float dot = warp_sum((a0 + a1) + (a2 + a3));
+            key = make_key(dot, (uint32_t)ix);
+        }
+        if (lane == 0) keys[c] = key;
+    }
+    __syncthreads();
+    block_bitonic(keys, Kp, 0, 2, Kp, tid, RESCORE_THREADS);
+    for (int t = tid; t < k_out; t += RESCORE_THREADS) {
+        const unsigned long long key = t < Kp ? keys[t] : 0ull;
+        const bool ok = key != 0ull;
+        out_scores[(size_t)q * k_out + t] = ok ? key_score(key) : -INFINITY;
+        out_idx[(size_t)q * k_out + t] = ok ? (int32_t)key_index(key) : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// full argsort of score rows
+// ---------------------------------------------------------------------------------------
+__global__ void sort_build_keys(const float* __restrict__ scores, long long N, long long ld, long long Npad,
+                                unsigned long long* __restrict__ keys) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (i >= Npad) return;
+    keys[(size_t)q * Npad + i] = i < N ? make_key(__ldg(scores + (size_t)q * ld + i), (uint32_t)i) : 0ull;
+}
+
+// sorts / merges one 4096-key tile in shared memory: phases kfirst..klast
+__global__ void __launch_bounds__(SEL_THREADS)
+sort_local_kernel(unsigned long long* __restrict__ keys, long long Npad, long long kfirst, long long klast) {
+    __shared__ unsigned long long buf[SEL_N];
+    const long long base = (long long)blockIdx.x * SEL_N;
+    unsigned long long* g = keys + (size_t)blockIdx.y * Npad + base;
+    for (int t = threadIdx.x; t < SEL_N; t += SEL_THREADS) buf[t] = g[t];
+    __syncthreads();
+    block_bitonic(buf, SEL_N, base, kfirst, klast, threadIdx.x, SEL_THREADS);
+    for (int t = threadIdx.x; t < SEL_N; t += SEL_THREADS) g[t] = buf[t];
+}
+
+// one compare-exchange stage with stride j >= 4096 in global memory
+__global__ void sort_global_stage(unsigned long long* __restrict__ keys, long long Npad, long long k, long long j) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (Npad >> 1)) return;
+    unsigned long long* g = keys + (size_t)blockIdx.y * Npad;
+    const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const long long l = i | j;
+    const bool desc = (i & k) == 0;
+    const unsigned long long a = g[i], b = g[l];
+    if ((a < b) == desc) { g[i] = b; g[l] = a; }
+}
+
+__global__ void sort_extract(const unsigned long long* __restrict__ keys, long long N, long long Npad,
+                             int32_t* __restrict__ out_idx, float* __restrict__ out_sorted) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (i >= N) return;
+    const unsigned long long key = keys[(size_t)q * Npad + i];
+    out_idx[(size_t)q * N + i] = (int32_t)key_index(key);
+    if (out_sorted) out_sorted[(size_t)q * N + i] = key_score(key);
+}
+
+static long long sort_npad(long long N) {
+    long long p = SEL_N;
+    while (p < N) p <<= 1;
+    return p;
+}
+
+}  // namespace cir
+
+using namespace cir;
+
+extern "C" int cir_topk_merge(const float* scores, const int32_t* idx, int G, int Q, int k, float* out_scores,
+                              int32_t* out_idx, int k_out, void* stream) {
+    CIR_REQUIRE(scores && idx && out_scores && out_idx, CIR_ERR_INVALID_ARG, "cir_topk_merge: null pointer");
+    CIR_REQUIRE(G >= 1 && Q >= 0 && k >= 1 && k_out >= 1, CIR_ERR_INVALID_ARG, "cir_topk_merge: bad shape");
+    CIR_REQUIRE(k_out + k <= SEL_N, CIR_ERR_UNSUPPORTED, "cir_topk_merge: k_out + k = %d exceeds %d", k_out + k, SEL_N);
+    if (Q == 0) return CIR_OK;
+    SelParams p{};
+    p.in_scores = scores; p.in_idx = idx; p.kin = k;
+    p.G = G; p.Q = Q; p.k = k_out;
+    p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = k_out; p.idx_offset = 0;
+    topk_select_kernel<1><<<Q, SEL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
+}
+
+extern "C" int cir_rescore_topk(const float* q32, int Q, const float* db32, int64_t N, int D, const int32_t* cand,
+                                int Kc, int32_t idx_offset, float* out_scores, int32_t* out_idx, int k_out,
+                                void* stream) {
+    CIR_REQUIRE(q32 && db32 && cand && out_scores && out_idx, CIR_ERR_INVALID_ARG, "cir_rescore_topk: null pointer");
+    CIR_REQUIRE(Q >= 0 && N > 0 && D > 0 && Kc >= 1 && k_out >= 1 && k_out <= Kc, CIR_ERR_INVALID_ARG,
+                "cir_rescore_topk: bad shape (Q=%d D=%d Kc=%d k_out=%d)", Q, D, Kc, k_out);
+    CIR_REQUIRE(Kc <= SEL_N, CIR_ERR_UNSUPPORTED, "cir_rescore_topk: Kc=%d exceeds %d", Kc, SEL_N);
+    if (Q == 0) return CIR_OK;
+    int Kp = 2;
+    while (Kp < Kc) Kp <<= 1;
+    const size_t smem = (size_t)Kp * 8 + (size_t)D * 4;
+    const DeviceInfo& dev = device_info();
+    CIR_REQUIRE((int)smem <= dev.max_smem_optin, CIR_ERR_UNSUPPORTED, "cir_rescore_topk: D=%d too large for shared memory", D);
+    if (smem > 48 * 1024)
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rescore_kernel<<<Q, RESCORE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(q32, db32, N, D, cand, Kc, Kp, idx_offset,
+                                                                                   out_scores, out_idx, k_out);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
+}
+
+extern "C" int cir_sort_rows_workspace_bytes(int Q, int64_t N, size_t* bytes) {
+    CIR_REQUIRE(bytes && Q > 0 && N > 0, CIR_ERR_INVALID_ARG, "cir_sort_rows_workspace_bytes: bad arguments");
+    *bytes = (size_t)Q * (size_t)sort_npad(N) * 8;
+    return CIR_OK;
+}
+
+extern "C" int cir_sort_rows_desc(const float* scores, int Q, int64_t N, int64_t ld, int32_t* out_idx, float* out_sorted,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+    CIR_REQUIRE(scores && out_idx && Q > 0 && N > 0 && ld >= N, CIR_ERR_INVALID_ARG, "cir_sort_rows_desc: bad arguments");
+    CIR_REQUIRE(N <= 0x7fffff00ll && Q <= 65535, CIR_ERR_UNSUPPORTED, "cir_sort_rows_desc: N or Q too large");
+    size_t need = 0;
+    cir_sort_rows_workspace_bytes(Q, N, &need);
+    CIR_REQUIRE(workspace && workspace_bytes >= need, CIR_ERR_WORKSPACE, "cir_sort_rows_desc: workspace %zu < %zu bytes",
+                workspace_bytes, need);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long Npad = sort_npad(N);
+    unsigned long long* keys = static_cast<unsigned long long*>(workspace);
+    int launches = 0;
+    {
+        dim3 grid((unsigned)((Npad + 255) / 256), Q);
+        sort_build_keys<<<grid, 256, 0, stream>>>(scores, N, ld, Npad, keys);
+        ++launches;
+    }
+    const dim3 tiles((unsigned)(Npad / SEL_N), Q);
+    sort_local_kernel<<<tiles, SEL_THREADS, 0, stream>>>(keys, Npad, 2, SEL_N);
+    ++launches;
+    for (long long k = 2ll * SEL_N; k <= Npad; k <<= 1) {
+        for (long long j = k >> 1; j >= SEL_N; j >>= 1) {
+            dim3 grid((unsigned)(((Npad >> 1) + 255) / 256), Q);
+            sort_global_stage<<<grid, 256, 0, stream>>>(keys, Npad, k, j);
+            ++launches;
+        }
+        sort_local_kernel<<<tiles, SEL_THREADS, 0, stream>>>(keys, Npad, k, k);
+        ++launches;
+    }
+    {
+        dim3 grid((unsigned)((N + 255) / 256), Q);
+        sort_extract<<<grid, 256, 0, stream>>>(keys, N, Npad, out_idx, out_sorted);
+        ++launches;
+    }
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch(launches);
+    return CIR_OK;
+}

@@ -1,0 +1,159 @@
+"""Hard-negative mining, alpha-QE / DBA and the whitening helpers vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import clustered_unit_rows
+from oracle import cirtorch_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_mining_golden_fixture(golden):
+    from cirtorch_b200.mining import mine_hard_negatives
+    g = golden("mining")
+    neg, avg = mine_hard_negatives(_dev(g["qvecs"]), _dev(g["poolvecs"]), g["clusters"].tolist(),
+                                   g["query_indices"].tolist(), g["idxs2images"], int(g["neg_num"]))
+    assert neg == g["negative_indices"].tolist()
+    assert abs(avg - float(g["avg_dist"])) < 1e-5
+
+
+def _mining_case(Q, P, D, n_clusters, n_images, seed):
+    rs = np.random.RandomState(seed)
+    clusters = rs.randint(0, n_clusters, size=n_images)
+    idxs2images = rs.permutation(n_images)[:P]
+    query_indices = rs.permutation(n_images)[:Q]
+    centres = rs.randn(n_clusters, D).astype(np.float32)
+    allv = centres[clusters] * 0.6 + rs.randn(n_images, D).astype(np.float32)
+    allv /= np.linalg.norm(allv, axis=1, keepdims=True)
+    return allv[query_indices].T.copy(), allv[idxs2images].T.copy(), clusters, query_indices, idxs2images
+
+
+@pytest.mark.parametrize("Q,P,D,ncl,nimg,nnum", [
+    (64, 1500, 128, 40, 4000, 5),
+    (200, 3000, 64, 12, 5000, 5),      # few clusters: long walks, forces the longer-list / full-rank fallback
+    (10, 200, 32, 8, 300, 3),
+])
+def test_mining_matches_oracle(Q, P, D, ncl, nimg, nnum):
+    from cirtorch_b200.mining import mine_hard_negatives
+    qv, pv, clusters, qidx, i2i = _mining_case(Q, P, D, ncl, nimg, seed=Q)
+    ref_neg, ref_avg = O.mine_hard_negatives(torch.from_numpy(qv), torch.from_numpy(pv), clusters.tolist(),
+                                             qidx.tolist(), i2i, nnum)
+    neg, avg = mine_hard_negatives(_dev(qv), _dev(pv), clusters, qidx, i2i, nnum)
+    if neg != ref_neg:
+        # only fp32 near-ties may reorder the walk: the sets must still carry equal scores
+        sims = pv.T.astype(np.float64) @ qv.astype(np.float64)
+        pos = {int(v): j for j, v in enumerate(i2i)}
+        for q, (a, b) in enumerate(zip(neg, ref_neg)):
+            sa = sorted(sims[pos[x], q] for x in a)
+            sb = sorted(sims[pos[x], q] for x in b)
+            np.testing.assert_allclose(sa, sb, atol=2e-6)
+    assert abs(avg - ref_avg) < 1e-4
+
+
+def test_mining_config3_full_size():
+    """BASELINE.json config 3 (2000 q x 20000 pool, nnum 5, D 2048): sets identical to the reference restatement."""
+    from cirtorch_b200.mining import mine_hard_negatives
+    qv, pv, clusters, qidx, i2i = _mining_case(2000, 20000, 2048, 700, 91642, seed=11)
+    neg, avg = mine_hard_negatives(_dev(qv), _dev(pv), clusters, qidx, i2i, 5)
+    sub = list(range(0, 2000, 40))                       # the oracle's full sort on a 50-query sample
+    ref_neg, _ = O.mine_hard_negatives(torch.from_numpy(qv[:, sub]), torch.from_numpy(pv), clusters.tolist(),
+                                       qidx[sub].tolist(), i2i, 5)
+    assert [neg[q] for q in sub] == ref_neg
+    pos_cluster = clusters
+    for q in range(2000):                                 # invariants on every query
+        cl = [pos_cluster[x] for x in neg[q]]
+        assert len(set(cl)) == 5 and pos_cluster[qidx[q]] not in cl
+
+
+def test_mining_exhausted_pool_raises():
+    from cirtorch_b200.mining import mine_hard_negatives
+    qv, pv, clusters, qidx, i2i = _mining_case(4, 50, 32, 3, 100, seed=5)
+    with pytest.raises(IndexError):
+        mine_hard_negatives(_dev(qv), _dev(pv), clusters, qidx, i2i, 5)     # only 2 foreign clusters exist
+
+
+def test_alpha_qe_and_dba_match_oracle():
+    from cirtorch_b200 import rerank, search as S
+    db, _ = clustered_unit_rows(3000, 128, 60, 0.6, seed=8)
+    q, _ = clustered_unit_rows(50, 128, 60, 0.6, seed=8)
+    ref = O.alpha_qe(q.T, db.T, k=10, alpha=3.0)
+    out = rerank.alpha_qe(_dev(q.T), _dev(db.T), k=10, alpha=3.0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5)
+    # the re-ranked lists agree with the oracle's re-search
+    s_ref, i_ref = O.topk(db.T, ref, 20)
+    s, i = S.search_topk(out.contiguous(), _dev(db.T), 20)
+    agree = (i.cpu().numpy() == i_ref).mean()
+    assert agree > 0.98
+    ref_d = O.dba(db.T[:, :800], k=5, alpha=3.0)
+    out_d = rerank.dba(_dev(db.T[:, :800].copy()), k=5, alpha=3.0)
+    np.testing.assert_allclose(out_d.cpu().numpy(), ref_d, atol=2e-5)
+    # k = 0 -> identity
+    idn = rerank.qe_aggregate_rows(_dev(q), _dev(db), torch.zeros((50, 1), dtype=torch.int32, device=DEV),
+                                   torch.zeros((50, 1), device=DEV), 0, 3.0)
+    np.testing.assert_allclose(idn.cpu().numpy(), q / (1 + 1e-6), atol=1e-6)
+
+
+def test_whiten_helpers_golden(golden):
+    from cirtorch_b200.utils import whiten as W
+    g = golden("whiten")
+    X = g["X"]
+    out = W.whitenapply(X, g["m"], g["P"])
+    assert isinstance(out, np.ndarray) and out.shape == g["apply"].shape
+    rel = np.linalg.norm(out - g["apply"], axis=0) / np.linalg.norm(g["apply"], axis=0)
+    assert rel.max() < 1e-4
+    out16 = W.whitenapply(X, g["m"], g["P"], dimensions=16)
+    rel = np.linalg.norm(out16 - g["apply_16"], axis=0) / np.linalg.norm(g["apply_16"], axis=0)
+    assert rel.max() < 1e-4
+    np.testing.assert_allclose(W.cholesky(g["S"]), g["L"], rtol=1e-9, atol=1e-12)
+    m, P = W.whitenlearn(X, g["qidxs"], g["pidxs"])
+    assert P.dtype == np.float64
+    np.testing.assert_allclose(m, g["m"], rtol=1e-10)
+    np.testing.assert_allclose(P.T @ P, g["P"].T @ g["P"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.abs(O.whitenapply(X, m, P)), np.abs(g["apply"]), rtol=1e-5, atol=1e-6)
+    mp, Pp = W.pcawhitenlearn(X)
+    np.testing.assert_allclose(mp, g["m_pca"], rtol=1e-6)
+    np.testing.assert_allclose(np.abs(O.whitenapply(X, mp, Pp)), np.abs(g["apply_pca"]), rtol=1e-4, atol=1e-5)
+
+
+def test_whitenapply_equals_tail_with_folded_bias():
+    """whitenapply(X, m, P) == the tail's Linear+L2N with W = P, b = -P m."""
+    from cirtorch_b200.utils import whiten as W
+    rs = np.random.RandomState(9)
+    X = rs.randn(256, 500).astype(np.float32)
+    X /= np.linalg.norm(X, axis=0, keepdims=True)
+    m, P = O.pcawhitenlearn(X.astype(np.float64))
+    ref = O.whitenapply(X.astype(np.float64), m, P)
+    out = W.whitenapply(torch.from_numpy(X).to(DEV), m, P)
+    assert torch.is_tensor(out) and out.is_cuda
+    rel = np.linalg.norm(out.cpu().numpy() - ref, axis=0) / np.linalg.norm(ref, axis=0)
+    assert rel.max() < 1e-4
+
+
+def test_extract_vectors_resnet50_end_to_end():
+    """Config-1 slice: torchvision ResNet50 (stock, random init) -> fused tail -> ranking, against the same
+    backbone followed by the oracle head, on a handful of small synthetic images."""
+    torchvision = pytest.importorskip("torchvision")
+    from cirtorch_b200.extract import resnet50_gem, extract_vectors
+    from cirtorch_b200 import search as S
+    torch.manual_seed(0)
+    net = resnet50_gem().to(DEV).eval()
+    imgs = [torch.randn(3, 256, 256) for _ in range(6)] + [torch.randn(3, 224, 192)]
+    vecs = extract_vectors(net, imgs, 256, None, batch_size=3)
+    assert vecs.shape == (2048, 7) and not vecs.is_cuda
+    with torch.no_grad():
+        fm = [net.body(im[None].to(DEV)).cpu() for im in imgs]
+    ref = torch.cat([O.head_forward(f, 3.0, 1e-6, net.ret_head.whiten.weight.detach().cpu(),
+                                    net.ret_head.whiten.bias.detach().cpu()) for f in fm], 1)
+    rel = (vecs - ref).norm(dim=0) / ref.norm(dim=0)
+    assert float(rel.max()) < 1e-4
+    ms = extract_vectors(net, imgs[:2], 256, None, ms=[1, 2 ** -0.5])
+    assert float(ms.norm(dim=0).max()) <= 1.0 + 1e-5          # mean of unit vectors, no re-normalisation (Q3)
+    scores, ranks = S.rank(vecs.to(DEV), vecs[:, :3].to(DEV))
+    s_ref, r_ref = O.rank(ref.numpy(), ref[:, :3].numpy())
+    assert (ranks[0].cpu().numpy() == np.arange(3)).all()

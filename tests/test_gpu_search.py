@@ -1,0 +1,208 @@
+"""Search / top-k / ranking kernels vs the CPU oracle (np.dot + np.argsort restatement of
+scripts/train_globalF.py:733-734).  Tolerances: bf16 scores 5e-4, bf16x3 and fp32 re-scored 2e-6
+(unit-norm D <= 2048); index lists identical except inside the tie window."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import clustered_unit_rows, check_topk_against_exact
+from oracle import cirtorch_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_BF16 = 5e-4
+TOL_X3 = 5e-6
+
+
+def _exact(q, db):
+    return q.astype(np.float64) @ db.astype(np.float64).T
+
+
+def _dev(a):
+    return torch.from_numpy(a).to(DEV)
+
+
+def test_pack_bf16_roundtrip():
+    from cirtorch_b200 import search as S
+    rs = np.random.RandomState(0)
+    x = rs.randn(37, 100).astype(np.float32)
+    p1 = S.pack_rows(_dev(x), "db", "bf16").float().cpu().numpy()
+    assert p1.shape == (37, 128)
+    ref = torch.from_numpy(x).bfloat16().float().numpy()
+    np.testing.assert_array_equal(p1[:, :100], ref)
+    assert (p1[:, 100:] == 0).all()
+    pq = S.pack_rows(_dev(x), "query", "bf16x3").float().cpu().numpy()
+    pd = S.pack_rows(_dev(x), "db", "bf16x3").float().cpu().numpy()
+    hi, lo = pq[:, :100], pq[:, 256:356]
+    np.testing.assert_array_equal(pq[:, 128:228], hi)
+    np.testing.assert_array_equal(pd[:, 128:228], lo)
+    np.testing.assert_array_equal(pd[:, 256:356], hi)
+    assert np.abs(hi + lo - x).max() < 2e-5 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("Q,N,D,k", [
+    (70, 4993, 2048, 100),     # rOxford5k shape (config 1)
+    (1, 300, 64, 10),
+    (129, 1000, 128, 5),       # two query tiles, one ragged
+    (33, 257, 192, 257 if 257 <= 512 else 512),   # k == N
+    (16, 50, 64, 64),          # k > N: -1 / -inf padding
+])
+def test_topk_matches_oracle(Q, N, D, k):
+    from cirtorch_b200 import search as S
+    db, _ = clustered_unit_rows(N, D, max(4, N // 50), 0.8, seed=1)
+    q, _ = clustered_unit_rows(Q, D, max(4, N // 50), 0.8, seed=1)   # same centres -> meaningful neighbours
+    ex = _exact(q, db)
+    kk = min(k, N)
+    for mode, rescore, tol, stol in (("bf16", False, TOL_BF16, TOL_BF16), ("bf16", True, TOL_X3, TOL_X3),
+                                     ("bf16x3", False, TOL_X3, TOL_X3)):
+        s, i = S.search_topk_rows(_dev(q), _dev(db), k, mode=mode, rescore=rescore)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        assert s.shape == (Q, k) and i.dtype == np.int32
+        if k > N:
+            assert (i[:, N:] == -1).all() and np.isneginf(s[:, N:]).all()
+        assert (np.diff(s[:, :kk], axis=1) <= 0).all(), "scores must be non-increasing"
+        if mode == "bf16" and rescore and k < N:
+            # candidates come from a bf16 scan: allow a swap at the boundary inside the bf16 window
+            check_topk_against_exact(i[:, :kk], s[:, :kk], ex, kk, TOL_BF16, stol)
+        else:
+            check_topk_against_exact(i[:, :kk], s[:, :kk], ex, kk, tol, stol)
+
+
+def test_golden_rank_fixture(golden):
+    """The committed fixture produced by the reference statements (np.dot + np.argsort)."""
+    from cirtorch_b200 import search as S
+    g = golden("rank")
+    V, Qv = g["database_vecs"], g["qvecs"]
+    scores, ranks = S.rank(_dev(V), _dev(Qv))
+    assert ranks.shape == g["ranks"].shape and ranks.dtype == torch.int64
+    np.testing.assert_allclose(scores.cpu().numpy(), g["scores"], atol=TOL_X3)
+    np.testing.assert_array_equal(ranks.cpu().numpy(), g["ranks"])          # no ties in this fixture
+    s, i = S.search_topk(_dev(Qv), _dev(V), 10, mode="bf16x3")
+    np.testing.assert_array_equal(i.cpu().numpy(), g["ranks"][:10])
+
+
+def test_full_rank_large_and_ties():
+    from cirtorch_b200 import search as S
+    rs = np.random.RandomState(5)
+    # exact ties: duplicated database rows -> (score desc, index asc) must hold
+    db = rs.randn(6000, 64).astype(np.float32)
+    db[3000:] = db[:3000]
+    q = rs.randn(9, 64).astype(np.float32)
+    sc = S.scores_dense_rows(_dev(q), _dev(db), mode="bf16x3")
+    order, srt = S.argsort_rows_desc(sc, return_sorted=True)
+    sc_h, order_h, srt_h = sc.cpu().numpy(), order.cpu().numpy(), srt.cpu().numpy()
+    np.testing.assert_allclose(sc_h, _exact(q, db), atol=1e-4 * np.abs(_exact(q, db)).max())
+    ref = np.argsort(-sc_h, axis=1, kind="stable")
+    np.testing.assert_array_equal(order_h, ref)
+    np.testing.assert_array_equal(srt_h, np.take_along_axis(sc_h, ref, 1))
+    # a power-of-two boundary and a multi-stage global merge
+    x = torch.randn(3, 20000, device=DEV)
+    o = S.argsort_rows_desc(x).cpu().numpy()
+    np.testing.assert_array_equal(o, np.argsort(-x.cpu().numpy(), axis=1, kind="stable"))
+
+
+def test_label_exclusion_and_tau0():
+    from cirtorch_b200 import search as S
+    db, lab = clustered_unit_rows(3000, 128, 30, 0.5, seed=2)
+    q, qlab = clustered_unit_rows(40, 128, 30, 0.5, seed=2)
+    ex = _exact(q, db)
+    ex_masked = np.where(lab[None, :] == qlab[:, None], -np.inf, ex)
+    qp, dbp = S.pack_rows(_dev(q), "query", "bf16x3"), S.pack_rows(_dev(db), "db", "bf16x3")
+    s, i = S.search_packed(qp, dbp, 20, q_label=_dev(qlab.astype(np.int32)), db_label=_dev(lab.astype(np.int32)))
+    i = i.cpu().numpy()
+    assert (lab[i] != qlab[:, None]).all()
+    check_topk_against_exact(i, s.cpu().numpy(), ex_masked, 20, TOL_X3)
+    # a valid lower bound of the k-th score must not change the result
+    kth = np.sort(ex, axis=1)[:, -20].astype(np.float32) - 1e-3
+    s2, i2 = S.search_packed(qp, dbp, 20, tau0=_dev(kth))
+    s3, i3 = S.search_packed(qp, dbp, 20)
+    assert torch.equal(i2, i3) and torch.equal(s2, s3)
+
+
+def test_merge_equals_global_topk():
+    """Shard algebra on one GPU: top-k(global) == merge(top-k per shard)."""
+    from cirtorch_b200 import search as S
+    db, _ = clustered_unit_rows(5000, 256, 50, 0.7, seed=3)
+    q, _ = clustered_unit_rows(65, 256, 50, 0.7, seed=3)
+    qd, dbd = _dev(q), _dev(db)
+    s_ref, i_ref = S.search_topk_rows(qd, dbd, 50, mode="bf16x3")
+    parts_s, parts_i = [], []
+    bounds = [0, 1200, 1201, 3700, 5000]       # ragged shards, one of a single row
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        s, i = S.search_topk_rows(qd, dbd[a:b].contiguous(), 50, mode="bf16x3", idx_offset=a)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = S.merge_topk(torch.stack(parts_s), torch.stack(parts_i), 50)
+    assert torch.equal(mi, i_ref)
+    assert torch.equal(ms, s_ref)
+
+
+def test_many_splits_small_k_large_n():
+    """More database tiles than SMs x a few: exercises multi-tile units, list compaction and the select rounds."""
+    from cirtorch_b200 import search as S
+    db, _ = clustered_unit_rows(200_000, 64, 500, 0.9, seed=4)
+    q, _ = clustered_unit_rows(200, 64, 500, 0.9, seed=4)
+    ex = _exact(q, db)
+    for k in (1, 10, 100, 400):
+        s, i = S.search_topk_rows(_dev(q), _dev(db), k, mode="bf16x3")
+        check_topk_against_exact(i.cpu().numpy(), s.cpu().numpy(), ex, k, TOL_X3)
+
+
+def test_equal_scores_flood():
+    """All database rows identical: every score ties; the lowest indices must win."""
+    from cirtorch_b200 import search as S
+    row = np.random.RandomState(6).randn(1, 64).astype(np.float32)
+    db = np.repeat(row, 5000, axis=0)
+    q = np.random.RandomState(7).randn(3, 64).astype(np.float32)
+    s, i = S.search_topk_rows(_dev(q), _dev(db), 100, mode="bf16")
+    np.testing.assert_array_equal(i.cpu().numpy(), np.tile(np.arange(100, dtype=np.int32), (3, 1)))
+
+
+def test_bad_arguments_raise():
+    from cirtorch_b200 import search as S
+    q = torch.zeros(4, 64, device=DEV)
+    with pytest.raises(ValueError):
+        S.search_topk_rows(q, torch.zeros(10, 64, device=DEV), 0)
+    with pytest.raises(ValueError):
+        S.search_topk_rows(q, torch.zeros(10, 64, device=DEV), 513)
+    with pytest.raises(ValueError):
+        S.search_packed(torch.zeros(4, 64, device=DEV, dtype=torch.bfloat16),
+                        torch.zeros(10, 128, device=DEV, dtype=torch.bfloat16), 5)
+
+
+@pytest.mark.parametrize("Q", [70, 1000])
+def test_million_row_database_properties(Q):
+    """BASELINE.json config 4 at full size (1M x 2048, top-100): too large for the CPU oracle in
+    seconds, so check size-independent properties: sortedness, fp32-exact returned scores, planted
+    neighbours found at rank 0, shard-merge == global, and a sampled exact check on 8 queries."""
+    from cirtorch_b200 import search as S
+    N, D, k = 1_000_000, 2048, 100
+    g = torch.Generator(device=DEV).manual_seed(0)
+    db = torch.empty((N, D), device=DEV)
+    for a in range(0, N, 100_000):
+        blk = torch.randn((100_000, D), device=DEV, generator=g)
+        db[a:a + 100_000] = blk / blk.norm(dim=1, keepdim=True)
+    planted = torch.randint(0, N, (Q,), device=DEV, generator=g)
+    q = db[planted] + 0.3 * torch.randn((Q, D), device=DEV, generator=g) / D ** 0.5
+    q = q / q.norm(dim=1, keepdim=True)
+    index = S.Index(db, mode="bf16")
+    s, i = index.search_rows(q, k)                      # bf16 scan + fp32 re-score
+    assert bool((i[:, 0].long() == planted).all())
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    got = (q[:, None, :] * db[i[:8].long()]).sum(-1) if Q >= 8 else None
+    np.testing.assert_allclose(s[:8].cpu().numpy(), got.cpu().numpy(), atol=2e-6)
+    # sampled exact check: brute-force scores of 8 queries in fp32 on the device, top-k by torch
+    ex = (q[:8] @ db.t())
+    ts, ti = torch.topk(ex, k, dim=1)
+    exn = ex.double().cpu().numpy()
+    check_topk_against_exact(i[:8].cpu().numpy(), s[:8].cpu().numpy(), exn, k, TOL_BF16, 5e-6)
+    # shard-merge == global (4 shards, raw bf16 lists so both sides see identical scores)
+    s_g, i_g = index.search_rows(q, k, rescore=False)
+    parts = []
+    for r in range(4):
+        a, b = r * N // 4, (r + 1) * N // 4
+        sh = S.Index.__new__(S.Index)
+        sh.mode, sh.N, sh.D, sh.row_offset, sh.packed, sh.rows32, sh.labels = "bf16", b - a, D, a, index.packed[a:b], None, None
+        parts.append(sh.search_rows(q, k, rescore=False))
+    ms, mi = S.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
+    assert torch.equal(mi, i_g) and torch.equal(ms, s_g)

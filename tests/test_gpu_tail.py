@@ -1,0 +1,152 @@
+"""Fused descriptor tail (cir_tail_fwd through the reference-shaped modules) vs the CPU oracle and
+the committed golden fixtures.  Tolerance: 1e-4 relative per descriptor (north-star, fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cirtorch_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-4
+
+
+def _rel(a, b, dim=0):
+    return float(((a - b).norm(dim=dim) / b.norm(dim=dim).clamp_min(1e-30)).max())
+
+
+def _head(dim, pooling="GeM", p=3.0):
+    from cirtorch_b200.modules.heads.global_head import globalHead
+    params = {"p": p, "eps": 1e-6} if pooling in ("GeM", "GeMmp") else {}
+    return globalHead(pooling={"name": pooling, "params": params}, normal={"name": "L2N", "params": {}}, dim=dim)
+
+
+def test_golden_fixtures(golden):
+    from cirtorch_b200.modules.pools import GeM, MAC, SPoC
+    from cirtorch_b200.modules.normalizations import L2N
+    g = golden("tail")
+    for c in "abcd":
+        x = torch.from_numpy(g[f"{c}_x"]).to(DEV)
+        p = float(g[f"{c}_p"])
+        head = _head(x.shape[1], p=p).to(DEV)
+        with torch.no_grad():
+            head.whiten.weight.copy_(torch.from_numpy(g[f"{c}_W"]))
+            head.whiten.bias.copy_(torch.from_numpy(g[f"{c}_b"]))
+            gem = GeM(p=p).to(DEV)(x)
+            assert gem.shape == g[f"{c}_gem"].shape
+            np.testing.assert_allclose(gem.cpu().numpy(), g[f"{c}_gem"], rtol=RTOL, atol=1e-7)
+            np.testing.assert_allclose(L2N()(gem).cpu().numpy(), g[f"{c}_l2n"], rtol=RTOL, atol=1e-7)
+            np.testing.assert_array_equal(MAC()(x).cpu().numpy(), g[f"{c}_mac"])
+            np.testing.assert_allclose(SPoC()(x).cpu().numpy(), g[f"{c}_spoc"], rtol=1e-5, atol=1e-8)
+            out = head(x)
+            assert out.shape == g[f"{c}_head"].shape
+            assert _rel(out.cpu(), torch.from_numpy(g[f"{c}_head"])) < RTOL
+            out2 = head(x, do_whitening=False)
+            assert _rel(out2.cpu(), torch.from_numpy(g[f"{c}_head_nowhiten"])) < RTOL
+
+
+@pytest.mark.parametrize("shape,p", [
+    ((64, 2048, 8, 8), 3.0),       # config-2 channel count, small maps
+    ((5, 2048, 32, 32), 3.0),      # config-2 map size
+    ((3, 2048, 32, 32), 2.7),      # learnable, non-integer exponent
+    ((7, 512, 19, 23), 3.0),       # HW % 4 != 0: scalar path
+    ((130, 96, 4, 4), 2.0),        # more images than one phase-B pass (64)
+    ((1, 64, 1, 1), 3.0),
+])
+def test_head_vs_oracle(shape, p):
+    torch.manual_seed(0)
+    n, c, h, w = shape
+    x = torch.relu(torch.randn(shape))
+    head = _head(c, p=p)
+    with torch.no_grad():
+        head.whiten.bias.normal_(0, 0.02)
+    ref = O.head_forward(x, p, 1e-6, head.whiten.weight.detach(), head.whiten.bias.detach())
+    ref_nw = O.head_forward(x, p, 1e-6, do_whitening=False)
+    head = head.to(DEV)
+    with torch.no_grad():
+        out = head(x.to(DEV))
+        out_nw = head(x.to(DEV), do_whitening=False)
+    assert out.shape == (c, n) and out.t().is_contiguous()
+    assert _rel(out.cpu(), ref) < RTOL
+    assert _rel(out_nw.cpu(), ref_nw) < RTOL
+    np.testing.assert_allclose(out.norm(dim=0).cpu().numpy(), 1.0, atol=1e-4)
+
+
+def test_pooling_variants():
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(4, 256, 16, 16))
+    for pooling in ("MAC", "SPoC"):
+        head = _head(256, pooling)
+        ref = O.head_forward(x, None, 1e-6, head.whiten.weight.detach(), head.whiten.bias.detach(), pooling=pooling)
+        with torch.no_grad():
+            out = head.to(DEV)(x.to(DEV))
+        assert _rel(out.cpu(), ref) < RTOL
+    head = _head(256, "GeMmp", p=3.0)
+    with torch.no_grad():
+        head.pool.p.copy_(torch.linspace(1.5, 4.5, 256))
+    ref = O.head_forward(x, head.pool.p.detach(), 1e-6, head.whiten.weight.detach(), head.whiten.bias.detach())
+    with torch.no_grad():
+        out = head.to(DEV)(x.to(DEV))
+    assert _rel(out.cpu(), ref) < RTOL
+
+
+def test_state_dict_keys_and_empty_batch():
+    head = _head(64)
+    assert set(head.state_dict().keys()) == {"pool.p", "whiten.weight", "whiten.bias"}
+    head = head.to(DEV)
+    out = head(torch.zeros(0, 64, 4, 4, device=DEV))
+    assert out.shape == (64, 0)
+
+
+def test_l2n_general_rank():
+    from cirtorch_b200.modules.normalizations import L2N
+    torch.manual_seed(2)
+    x = torch.randn(3, 40, 5, 6)
+    ref = O.l2n(x)
+    out = L2N()(x.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_gradients_match_autograd():
+    """Training: p, W, b and x receive the gradients of the reference formula."""
+    torch.manual_seed(3)
+    x = torch.relu(torch.randn(6, 32, 5, 5)) + 0.01
+    head = _head(32, p=2.5)
+    xr = x.clone().requires_grad_(True)
+    ref = O.head_forward(xr, head.pool.p, 1e-6, head.whiten.weight, head.whiten.bias)
+    tgt = torch.randn_like(ref)
+    (ref * tgt).sum().backward()
+    gref = [xr.grad.clone(), head.pool.p.grad.clone(), head.whiten.weight.grad.clone(), head.whiten.bias.grad.clone()]
+    head.zero_grad()
+    head = head.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    out = head(xg)
+    (out * tgt.to(DEV)).sum().backward()
+    got = [xg.grad, head.pool.p.grad, head.whiten.weight.grad, head.whiten.bias.grad]
+    for a, b in zip(got, gref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=2e-3, atol=1e-6)
+
+
+def test_cpu_tensor_is_rejected():
+    from cirtorch_b200._lib import CirError
+    head = _head(16)
+    with pytest.raises(CirError):
+        head(torch.zeros(1, 16, 2, 2))
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 at full size: unit norms, batch-order equivariance, determinism."""
+    torch.manual_seed(4)
+    x = torch.relu(torch.randn(64, 2048, 32, 32, device=DEV))
+    head = _head(2048).to(DEV)
+    with torch.no_grad():
+        a = head(x)
+        b = head(x)
+        perm = torch.randperm(64, device=DEV)
+        c = head(x[perm].contiguous())
+    assert torch.equal(a, b)
+    np.testing.assert_allclose(a.norm(dim=0).cpu().numpy(), 1.0, atol=1e-4)
+    assert float((a[:, perm] - c).abs().max()) < 1e-6
+    # a few images against the oracle at full channel count / map size
+    ref = O.head_forward(x[:4].cpu(), 3.0, 1e-6, head.whiten.weight.detach().cpu(), head.whiten.bias.detach().cpu())
+    assert _rel(a[:, :4].cpu(), ref) < RTOL

@@ -1,0 +1,79 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/cir_b200.h, the
+argument validation of the host layer, and that nothing falls back to the CPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cir_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cir_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, "binding missing for " + name
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert lib.cir_version() >= 100
+
+
+def test_no_cpu_fallback():
+    from cirtorch_b200._lib import CirError
+    from cirtorch_b200.modules.pools import GeM
+    from cirtorch_b200.modules.normalizations import L2N
+    from cirtorch_b200 import search as S
+    x = torch.rand(2, 8, 4, 4)
+    with pytest.raises(CirError):
+        GeM()(x)
+    with pytest.raises(CirError):
+        L2N()(x)
+    with pytest.raises(CirError):
+        S.search_topk(torch.rand(64, 3), torch.rand(64, 10), 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "image-retrieval-for-image-based-localization_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_registries_and_signatures_mirror_reference():
+    from cirtorch_b200.modules.pools import POOLING_LAYERS, GeM, GeMmp
+    from cirtorch_b200.modules.normalizations import NORMALIZATION_LAYERS
+    from cirtorch_b200.modules.heads.global_head import globalHead
+    from cirtorch_b200.layers.pooling import GeM as GeM2
+    import inspect
+    assert {"MAC", "SPoC", "GeM", "GeMmp"} <= set(POOLING_LAYERS) and "L2N" in NORMALIZATION_LAYERS
+    assert GeM is GeM2
+    assert list(inspect.signature(GeM.__init__).parameters)[1:] == ["p", "eps"]
+    assert list(inspect.signature(GeMmp.__init__).parameters)[1:] == ["p", "mp", "eps"]
+    assert list(inspect.signature(globalHead.__init__).parameters)[1:] == ["pooling", "normal", "dim", "norm_act"]
+    assert list(inspect.signature(globalHead.forward).parameters)[1:] == ["x", "do_whitening"]
+    head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=32)
+    assert set(head.state_dict()) == {"pool.p", "whiten.weight", "whiten.bias"}
+    assert float(head.whiten.bias.abs().max()) == 0.0 and float(head.whiten.weight.std()) < 0.05
+
+
+def test_shard_bounds_partition():
+    from cirtorch_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 1_000_000, 4993):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
