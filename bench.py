@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the global-descriptor retrieval hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-search]
+
+Headline line (`metric` = descriptors/s): one step = one pass of the fused GeM+L2N+whiten+L2N tail
+over a batch of 64 x 2048 x 32 x 32 fp32 layer-4 maps (BASELINE.json configs[1]), whitening
+2048 -> 2048, synthetic data, random-init weights.  N > 1 (torchrun): data parallel, one batch per
+rank per step (weak scaling).  The same JSON line carries, under "search", queries/s of the
+1M x 2048 top-100 search (configs[3]) with the database row-sharded over the N GPUs (strong
+scaling: one NCCL all_gather of the per-query lists + merge), and the roofline of both kernels.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port of
+globalHead.forward, all host threads) -- on rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "image-retrieval-for-image-based-localization_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+B, C, H, W, DOUT = 64, 2048, 32, 32, 2048
+TAIL_BYTES = B * C * H * W * 4 + DOUT * C * 4 + DOUT * 4 + B * DOUT * 4          # 554,180,608
+DB_N, DB_D, TOPK = 1_000_000, 2048, 100
+METRIC = "descriptors/s (GeM+whiten tail) & queries/s vs 1M×2048 DB at 1/2/4/8 B200, %roofline"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """NVML clocks / throttle reasons sampled in a thread while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples = []
+        self.stop = False
+        self.mark = 0
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.mark, mhz, r))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def finish(self):
+        self.stop = True
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.t.join(1.0)
+        timed = [s for s in self.samples if s[0] == 1] or self.samples[-5:]
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        bits = 0
+        for s in timed:
+            bits |= s[2]
+        reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
+        mhz = sorted(s[1] for s in timed)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(timed)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def timed_region(fn, steps, warmup, world, sampler=None):
+    """W untimed steps, then exactly K timed steps between barrier + synchronize; max over ranks (device time)."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark = 1
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.mark = 2
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
+
+
+def make_head(dev):
+    from cirtorch_b200.modules.heads.global_head import globalHead
+    torch.manual_seed(0)
+    head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}},
+                      normal={"name": "L2N", "params": {}}, dim=DOUT)
+    return head.to(dev).eval()
+
+
+def cpu_tail_baseline(budget_s=12.0, max_iters=30):
+    """The oracle port of globalHead.forward on the host cores, batch 64 x 2048 x 32 x 32."""
+    from oracle import cirtorch_oracle as O
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, H, W))
+    Wt = torch.empty(DOUT, C)
+    torch.nn.init.xavier_normal_(Wt, 0.1)
+    b = torch.zeros(DOUT)
+    O.head_forward(x, 3.0, 1e-6, Wt, b)              # warm-up
+    t0 = time.perf_counter()
+    it = 0
+    while it < max_iters and (time.perf_counter() - t0 < budget_s or it < 2):
+        O.head_forward(x, 3.0, 1e-6, Wt, b)
+        it += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * it / dt, "unit": "descriptors/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d batches of %dx%dx%dx%d fp32 through oracle.head_forward (torch CPU eager, %d threads)"
+                      % (it, B, C, H, W, torch.get_num_threads())}
+
+
+def cpu_search_baseline(n_rows=100_000, q=70, budget_s=10.0):
+    """np.dot + np.argsort (scripts/train_globalF.py:733-734) on a 100k-row slice of the database."""
+    from oracle import cirtorch_oracle as O
+    rs = np.random.RandomState(0)
+    db = rs.randn(DB_D, n_rows).astype(np.float32)
+    qs = rs.randn(DB_D, q).astype(np.float32)
+    t0 = time.perf_counter()
+    it = 0
+    while it < 3 and (time.perf_counter() - t0 < budget_s or it < 1):
+        O.rank(db, qs)
+        it += 1
+    dt = (time.perf_counter() - t0) / it
+    return {"value": q / (dt * DB_N / n_rows), "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "np.dot + np.argsort, %d queries x %d rows x %d, time scaled linearly to 1M rows" % (q, n_rows, DB_D)}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import cirtorch_oracle as O
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(B, C, H, W))
+    Wt = torch.empty(DOUT, C)
+    torch.nn.init.xavier_normal_(Wt, 0.1)
+    b = torch.zeros(DOUT)
+    for _ in range(args.warmup):
+        O.head_forward(x, 3.0, 1e-6, Wt, b)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.head_forward(x, 3.0, 1e-6, Wt, b)
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    threads = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "descriptors/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fused tail: batch 64x2048x32x32 fp32 maps -> GeM(p=3)+L2N+whiten 2048->2048+L2N",
+                   "note": "reference CPU path = oracle port of globalHead.forward (global_head.py:52-67), torch CPU eager"},
+        "cpu_baseline": {"value": val, "unit": "descriptors/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of one 64-image batch, %d host threads" % (args.steps, threads)},
+        "e2e": {"value": val, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def bench_search(dev, rank, world, pk, steps, warmup):
+    """1M x 2048 database row-sharded over the ranks, top-100: 10k-query batch (tensor-bound) and 70 queries (HBM-bound)."""
+    import torch.distributed as dist
+    from cirtorch_b200 import search as S, parallel as P, _lib
+    lo, hi = P.shard_bounds(DB_N, world, rank)
+    n_loc = hi - lo
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    dbp = torch.empty((n_loc, DB_D), dtype=torch.bfloat16, device=dev)
+    rows32 = torch.empty((n_loc, DB_D), dtype=torch.float32, device=dev)
+    for a in range(0, n_loc, 62_500):
+        b = min(n_loc, a + 62_500)
+        blk = torch.randn((b - a, DB_D), device=dev, generator=g)
+        rows32[a:b] = blk / blk.norm(dim=1, keepdim=True)
+    S.pack_rows(rows32, "db", "bf16", out=dbp)
+    gq = torch.Generator(device=dev).manual_seed(99)
+    out = {}
+    for name, Q in (("q10k", 10_000), ("q70", 70)):
+        q32 = torch.randn((Q, DB_D), device=dev, generator=gq)
+        q32 = q32 / q32.norm(dim=1, keepdim=True)
+        qp = S.pack_rows(q32, "query", "bf16")
+
+        def step_local():
+            return S.search_packed(qp, dbp, TOPK, idx_offset=lo)
+
+        def step():
+            s, i = step_local()
+            if world > 1:
+                s_all, i_all = P.gather_topk(s, i)
+                s, i = S.merge_topk(s_all, i_all, TOPK)
+            return s, i
+
+        k_steps = max(3, steps // 10) if Q >= 1000 else max(5, steps)
+        _lib.launch_count(reset=True)
+        ms = timed_region(step, k_steps, max(3, warmup), world) / k_steps
+        launches = _lib.launch_count()
+        ms_kernel = timed_region(step_local, k_steps, 3, world) / k_steps
+        flops = 2.0 * Q * n_loc * DB_D
+        res = {"queries_per_s": Q / (ms * 1e-3), "ms_per_search": ms, "ms_local_kernels": ms_kernel,
+               "steps": k_steps, "launches_per_search": launches // (k_steps + max(3, warmup)), "Q": Q, "N": DB_N, "k": TOPK}
+        if Q >= 1000:
+            tf = flops / (ms_kernel * 1e-3) / 1e12
+            res["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                               "frac": tf / pk["bf16_tflops_sustained"], "traffic": None,
+                               "note": "per GPU: 2*Q*N_local*D flop / local search time (GEMM + top-k select); peak = "
+                                       + pk["src"] + " sustained cuBLAS bf16"}
+        else:
+            gb = (n_loc * DB_D * 2 + Q * DB_D * 2 + Q * TOPK * 8) / (ms_kernel * 1e-3) / 1e9
+            res["roofline"] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": gb / pk["hbm_gbs"], "traffic": None,
+                               "note": "per GPU: bf16 shard scan bytes / local search time; peak = " + pk["src"] + " copy bandwidth"}
+        # end to end through the public API with host buffers: H2D queries, pack, scan, fp32 re-score, D2H lists
+        if name == "q10k":
+            index = S.Index.__new__(S.Index)
+            index.mode, index.N, index.D, index.row_offset, index.packed, index.rows32, index.labels = \
+                "bf16", n_loc, DB_D, lo, dbp, rows32, None
+            q_host = q32.cpu().pin_memory()
+            s_host = torch.empty((Q, TOPK), dtype=torch.float32).pin_memory()
+            i_host = torch.empty((Q, TOPK), dtype=torch.int32).pin_memory()
+
+            def step_e2e():
+                qd = q_host.to(dev, non_blocking=True)
+                s, i = index.search_rows(qd, TOPK)            # bf16 scan of top-128 + exact fp32 re-score
+                if world > 1:
+                    s_all, i_all = P.gather_topk(s, i)
+                    s, i = S.merge_topk(s_all, i_all, TOPK)
+                s_host.copy_(s, non_blocking=True)
+                i_host.copy_(i, non_blocking=True)
+
+            ms_e = timed_region(step_e2e, k_steps, 3, world) / k_steps
+            res["e2e"] = {"value": Q / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * DB_D * 4,
+                          "d2h_bytes_per_step": Q * TOPK * 8, "includes": "fp32 re-score of 128 candidates"}
+        out[name] = res
+        del q32, qp
+    del dbp, rows32
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cirtorch_b200 import _lib
+    _lib.load()
+    pk = peaks()
+    head = make_head(dev)
+
+    # two input batches (2 x 512 MiB) used alternately: every step streams data that is not in the 126 MB L2
+    g = torch.Generator(device=dev).manual_seed(rank)
+    xs = [torch.relu(torch.randn((B, C, H, W), device=dev, generator=g)) for _ in range(2)]
+    state = {"i": 0}
+
+    def step():
+        state["i"] ^= 1
+        with torch.no_grad():
+            return head(xs[state["i"]])
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(3):
+        step()
+    _lib.launch_count(reset=True)
+    ms = timed_region(step, args.steps, args.warmup, world, sampler)
+    launches = _lib.launch_count() - args.warmup
+    clocks = sampler.finish() if sampler else None
+    ms_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # end to end through the module API with HOST buffers: H2D of the maps, the fused tail, D2H of the descriptors
+    x_host = [x.cpu().pin_memory() for x in xs[:1]]
+    d_host = torch.empty((B, DOUT), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty_like(xs[0])
+
+    def step_e2e():
+        x_dev.copy_(x_host[0], non_blocking=True)
+        with torch.no_grad():
+            d = head(x_dev)
+        d_host.copy_(d.t(), non_blocking=True)
+
+    e_steps = max(3, min(args.steps, 10))
+    ms_e = timed_region(step_e2e, e_steps, 3, world)
+    e2e = {"value": world * B * e_steps / (ms_e * 1e-3), "unit": "descriptors/s",
+           "h2d_bytes_per_step": B * C * H * W * 4, "d2h_bytes_per_step": B * DOUT * 4}
+    del x_host, x_dev
+    achieved = TAIL_BYTES / (ms_step * 1e-3) / 1e9
+
+    search = None
+    if not args.no_search:
+        del xs
+        torch.cuda.empty_cache()
+        search = bench_search(dev, rank, world, pk, args.steps, args.warmup)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "descriptors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fused tail: batch 64x2048x32x32 fp32 maps -> GeM(p=3)+L2N+whiten 2048->2048+L2N "
+                                   "(BASELINE.json configs[1]); one batch per GPU per step",
+                       "l2": "inputs larger than L2: two 512 MiB batches used alternately",
+                       "search_workload": "1M x 2048 bf16 database row-sharded over the GPUs, top-100, 10k-query batch and 70 queries "
+                                          "(configs[3]); strong scaling"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                         "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth" % pk["src"]},
+            "search": search,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_tail_baseline()
+            if search is not None:
+                line["search"]["cpu_baseline"] = cpu_search_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

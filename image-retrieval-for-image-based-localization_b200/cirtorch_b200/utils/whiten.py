@@ -74,11 +74,19 @@ def _eig_desc(M):
     return w[order], V[:, order]
 
 
+def _mean_like_numpy(X, Xd):
+    """Row means in X's own precision (numpy keeps fp32 for fp32 input), returned as fp64."""
+    src_dtype = X.dtype if torch.is_tensor(X) else torch.from_numpy(np.asarray(X)[:0]).dtype
+    if src_dtype == torch.float32:
+        return Xd.float().mean(dim=1, keepdim=True).double()
+    return Xd.mean(dim=1, keepdim=True)
+
+
 def pcawhitenlearn(X):
     """whiten.py:14-30 (unsupervised PCA whitening).  X: D x N -> (m D x 1, P D x D)."""
     Xd = _to_dev(X, torch.float64)
     N = Xd.shape[1]
-    m = Xd.mean(dim=1, keepdim=True)
+    m = _mean_like_numpy(X, Xd)
     Xc = Xd - m
     cov = Xc @ Xc.t()
     cov = (cov + cov.t()) / (2 * N)
@@ -92,9 +100,9 @@ def whitenlearn(X, qidxs, pidxs):
     Xd = _to_dev(X, torch.float64)
     q = torch.as_tensor(np.asarray(qidxs), dtype=torch.long, device=Xd.device)
     p = torch.as_tensor(np.asarray(pidxs), dtype=torch.long, device=Xd.device)
-    m = Xd[:, q].mean(dim=1, keepdim=True)
+    m = _mean_like_numpy(X, Xd[:, q])
     df = Xd[:, q] - Xd[:, p]
-    S = (df @ df.t()) / df.shape[1]
+    S = (df @ df.t()) / df.shape[1]            # fp64 here; the reference forms S in X's precision
     P = torch.linalg.inv(_to_dev(cholesky(S), torch.float64))
     df = P @ (Xd - m)
     _, V = _eig_desc(df @ df.t())

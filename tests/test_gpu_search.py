@@ -1,6 +1,10 @@
 """Search / top-k / ranking kernels vs the CPU oracle (np.dot + np.argsort restatement of
 scripts/train_globalF.py:733-734).  Tolerances: bf16 scores 5e-4, bf16x3 and fp32 re-scored 2e-6
-(unit-norm D <= 2048); index lists identical except inside the tie window."""
+(unit-norm D <= 2048); index lists identical except inside the tie window.
+
+Measured on B200: the tcgen05 fp32 accumulator truncates instead of rounding, so a K = 3 x 2048 bf16x3
+dot product of magnitude ~0.7 carries up to ~1e-5 absolute error (384 sequential accumulations x 2^-24);
+TOL_X3 states that.  Lists that must be fp32-exact go through the fp32 re-score (TOL_F32)."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +15,8 @@ from oracle import cirtorch_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL_BF16 = 5e-4
-TOL_X3 = 5e-6
+TOL_X3 = 2e-5
+TOL_F32 = 2e-6
 
 
 def _exact(q, db):
@@ -53,7 +58,8 @@ def test_topk_matches_oracle(Q, N, D, k):
     q, _ = clustered_unit_rows(Q, D, max(4, N // 50), 0.8, seed=1)   # same centres -> meaningful neighbours
     ex = _exact(q, db)
     kk = min(k, N)
-    for mode, rescore, tol, stol in (("bf16", False, TOL_BF16, TOL_BF16), ("bf16", True, TOL_X3, TOL_X3),
+    tol_bf16 = TOL_BF16 * (2048.0 / D) ** 0.5      # bf16 rounding noise of unit-norm rows grows as 1/sqrt(D)
+    for mode, rescore, tol, stol in (("bf16", False, tol_bf16, tol_bf16), ("bf16", True, TOL_F32, TOL_F32),
                                      ("bf16x3", False, TOL_X3, TOL_X3)):
         s, i = S.search_topk_rows(_dev(q), _dev(db), k, mode=mode, rescore=rescore)
         s, i = s.cpu().numpy(), i.cpu().numpy()
@@ -63,7 +69,7 @@ def test_topk_matches_oracle(Q, N, D, k):
         assert (np.diff(s[:, :kk], axis=1) <= 0).all(), "scores must be non-increasing"
         if mode == "bf16" and rescore and k < N:
             # candidates come from a bf16 scan: allow a swap at the boundary inside the bf16 window
-            check_topk_against_exact(i[:, :kk], s[:, :kk], ex, kk, TOL_BF16, stol)
+            check_topk_against_exact(i[:, :kk], s[:, :kk], ex, kk, tol_bf16, stol)
         else:
             check_topk_against_exact(i[:, :kk], s[:, :kk], ex, kk, tol, stol)
 
@@ -189,7 +195,7 @@ def test_million_row_database_properties(Q):
     s, i = index.search_rows(q, k)                      # bf16 scan + fp32 re-score
     assert bool((i[:, 0].long() == planted).all())
     assert bool((s[:, 1:] <= s[:, :-1]).all())
-    got = (q[:, None, :] * db[i[:8].long()]).sum(-1) if Q >= 8 else None
+    got = (q[:8, None, :] * db[i[:8].long()]).sum(-1)
     np.testing.assert_allclose(s[:8].cpu().numpy(), got.cpu().numpy(), atol=2e-6)
     # sampled exact check: brute-force scores of 8 queries in fp32 on the device, top-k by torch
     ex = (q[:8] @ db.t())
