@@ -170,6 +170,9 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
+            // queries: small and re-read for every database tile -> keep; database: streamed.  With several
+            // query tiles the database tiles are shared through L2 by the CTAs of the same split (evict_last
+            // measured 15 % faster than evict_normal on 10k x 1M); with one query tile they are read once.
             const uint64_t pol_a = policy_evict_last();
             const uint64_t pol_b = P.b_evict_first ? policy_evict_first() : policy_evict_last();
             int stage = 0;
@@ -422,13 +425,34 @@ static int check_operands(const char* who, const void* q, int Q, const void* db,
 
 using namespace cir;
 
+// Warm start of the running thresholds: the k-th best score of every query over the first n0 database
+// rows is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
+// (the expensive part of the epilogue: measured 53.6 ms -> 30.9 ms on 10k x 1M with an exact tau0).
+static int sample_rows(int Q, long long N, int k) {
+    const int n0 = Q <= 2048 ? KTH_MAX_N : KTH_MAX_N / 2;
+    if (N < 8ll * n0 || k > n0 / 8) return 0;
+    return n0;
+}
+
+struct SearchWs {
+    size_t lists, counts, tau, dense, total;
+};
+static SearchWs search_ws_layout(const SearchPlan& plan, int Q, int cap, int n0) {
+    SearchWs w{};
+    w.lists = 0;
+    w.counts = w.lists + align_up((size_t)plan.S * plan.Qpad * cap * 8, 256);
+    w.tau = w.counts + align_up((size_t)plan.S * plan.Qpad * 4, 256);
+    w.dense = w.tau + align_up((size_t)plan.Qpad * 4, 256);
+    w.total = w.dense + align_up((size_t)Q * n0 * 4, 256);
+    return w;
+}
+
 extern "C" int cir_search_workspace_bytes(int Q, int64_t N, int Kd, int k, size_t* bytes) {
     (void)Kd;
     CIR_REQUIRE(bytes && Q > 0 && N > 0 && k >= 1 && k <= SEARCH_MAX_K, CIR_ERR_INVALID_ARG,
                 "cir_search_workspace_bytes: bad arguments (Q=%d N=%lld k=%d, k <= %d)", Q, (long long)N, k, SEARCH_MAX_K);
     const SearchPlan plan = plan_search(Q, N, device_info().num_sms);
-    const int cap = search_cap_for_k(k);
-    *bytes = align_up((size_t)plan.S * plan.Qpad * cap * 8, 256) + align_up((size_t)plan.S * plan.Qpad * 4, 256);
+    *bytes = search_ws_layout(plan, Q, search_cap_for_k(k), sample_rows(Q, N, k)).total;
     return CIR_OK;
 }
 
@@ -436,7 +460,6 @@ extern "C" int cir_search_topk(const void* q, int Q, const void* db, int64_t N, 
                                const int32_t* q_label, const int32_t* db_label, float* out_scores, int32_t* out_idx,
                                int32_t idx_offset, void* workspace, size_t workspace_bytes, unsigned flags,
                                void* stream) {
-    (void)flags;
     int rc = check_operands("cir_search_topk", q, Q, db, N, Kd);
     if (rc) return rc;
     CIR_REQUIRE(k >= 1 && k <= SEARCH_MAX_K, CIR_ERR_UNSUPPORTED, "cir_search_topk: k=%d outside [1, %d]", k, SEARCH_MAX_K);
@@ -449,11 +472,29 @@ extern "C" int cir_search_topk(const void* q, int Q, const void* db, int64_t N, 
                 workspace_bytes, need);
     CIR_REQUIRE(((uintptr_t)workspace & 15) == 0, CIR_ERR_INVALID_ARG, "cir_search_topk: workspace must be 16 B aligned");
     const SearchPlan plan = plan_search(Q, N, device_info().num_sms);
+    const int n0_ws = sample_rows(Q, N, k);
+    const SearchWs w = search_ws_layout(plan, Q, search_cap_for_k(k), n0_ws);
+    char* ws = static_cast<char*>(workspace);
+    const int n0 = (tau0 || q_label || (flags & CIR_SEARCH_NO_PREPASS)) ? 0 : n0_ws;
+    if (n0 > 0) {
+        // pre-pass: dense scores of the first n0 rows, then the k-th largest per query
+        float* dense = reinterpret_cast<float*>(ws + w.dense);
+        float* tau = reinterpret_cast<float*>(ws + w.tau);
+        SearchParams D{};
+        D.dense_out = dense;
+        D.dense_ld = n0;
+        rc = launch_search(MODE_DENSE, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
+                           static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+        rc = launch_row_kth_largest(dense, Q, n0, n0, k, tau, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+        tau0 = tau;
+    }
     SearchParams P{};
     P.k = k;
     P.cap = search_cap_for_k(k);
-    P.lists = static_cast<unsigned long long*>(workspace);
-    P.counts = reinterpret_cast<int*>(static_cast<char*>(workspace) + align_up((size_t)plan.S * plan.Qpad * P.cap * 8, 256));
+    P.lists = reinterpret_cast<unsigned long long*>(ws + w.lists);
+    P.counts = reinterpret_cast<int*>(ws + w.counts);
     P.tau0 = tau0;
     P.q_label = q_label;
     P.db_label = db_label;

@@ -27,6 +27,7 @@ constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_JMAX = 16;    // output dims per phase-B chunk
 constexpr int TAIL_KC = 2048;    // K extent of the W slice staged in shared memory
 constexpr int TAIL_IMG = 4;      // images per warp in phase B
+constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;   // debug time stamps: up to 1024 CTAs x 8 slots
 
 struct TailParams {
     const float* x;
@@ -46,7 +47,16 @@ struct TailParams {
     int jch, n_chunks;
     unsigned flags;
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
+    unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
 };
+
+__device__ __forceinline__ void stamp(const TailParams& P, int slot) {
+    if (P.stamps && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.stamps[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ float fast_lg2(float x) {
     float r;
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
         cp_async_commit();
     };
 
+    stamp(P, 0);
     int staged_chunk = -1, staged_kc0 = -1;
     if (whiten && (int)blockIdx.x < P.n_chunks) {
         stage_W(blockIdx.x, 0);            // lands while phase A streams the map
@@ -242,9 +253,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
             }
         }
     }
+    stamp(P, 1);
     if (pool_only) return;
 
     grid.sync();
+    stamp(P, 2);
 
     // ------------------------------------------------------------------ no whitening
     if (!whiten) {
@@ -268,6 +281,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
     }
 
     // ------------------------------------------------------------------ phase B
+    // Every CTA reads all pooled vectors from L2; CTAs start at different K offsets so that they do not
+    // all hit the same L2 lines at the same moment, and each lane prefetches its next 4 x float4 while it
+    // multiplies the current ones.
     for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
         const int j0 = chunk * P.jch;
         const int J = min(P.jch, P.D_out - j0);
@@ -291,23 +307,38 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
                 cp_async_wait_all();
                 __syncthreads();
                 const int kw = min(TAIL_KC, P.C - kc0);
+                const int iters = (kw + 127) >> 7;
                 if (nb < P.N) {
-                    for (int k = lane * 4; k < kw; k += 128) {
-                        float4 g[TAIL_IMG];
+                    const float* gbase = P.pooled + (size_t)nb * P.pooled_ld + kc0 + lane * 4;
+                    auto load_g = [&](int it, float4 (&g)[TAIL_IMG]) {
+                        const int k = it * 128 + lane * 4;
 #pragma unroll
                         for (int i = 0; i < TAIL_IMG; ++i) {
                             g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (nb + i < P.N)
-                                g[i] = __ldcg(reinterpret_cast<const float4*>(
-                                    P.pooled + (size_t)(nb + i) * P.pooled_ld + kc0 + k));
-                            ss[i] += dot4(g[i], g[i]);
+                            if (k < kw && nb + i < P.N)
+                                g[i] = __ldcg(reinterpret_cast<const float4*>(gbase + (size_t)i * P.pooled_ld + it * 128));
                         }
+                    };
+                    int it = (int)(blockIdx.x % (unsigned)iters);
+                    float4 g_next[TAIL_IMG];
+                    load_g(it, g_next);
+                    for (int t = 0; t < iters; ++t) {
+                        float4 g[TAIL_IMG];
 #pragma unroll
-                        for (int j = 0; j < TAIL_JMAX; ++j) {
-                            if (j < J) {
-                                const float4 w = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + k]);
+                        for (int i = 0; i < TAIL_IMG; ++i) g[i] = g_next[i];
+                        const int k = it * 128 + lane * 4;
+                        if (++it == iters) it = 0;
+                        if (t + 1 < iters) load_g(it, g_next);
+                        if (k < kw) {
 #pragma unroll
-                                for (int i = 0; i < TAIL_IMG; ++i) acc[i][j] += dot4(w, g[i]);
+                            for (int i = 0; i < TAIL_IMG; ++i) ss[i] += dot4(g[i], g[i]);
+#pragma unroll
+                            for (int j = 0; j < TAIL_JMAX; ++j) {
+                                if (j < J) {
+                                    const float4 w = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + k]);
+#pragma unroll
+                                    for (int i = 0; i < TAIL_IMG; ++i) acc[i][j] += dot4(w, g[i]);
+                                }
                             }
                         }
                     }
@@ -339,30 +370,46 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
         }
     }
 
+    stamp(P, 3);
     grid.sync();
+    stamp(P, 4);
 
     // ------------------------------------------------------------------ phase C: second L2N
-    for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-        const int j0 = chunk * P.jch;
-        const int J = min(P.jch, P.D_out - j0);
-        for (int n0 = 0; n0 < P.N; n0 += TAIL_WARPS * TAIL_IMG) {
-            const int nb = n0 + warp * TAIL_IMG;
-#pragma unroll
-            for (int i = 0; i < TAIL_IMG; ++i) {
-                const int n = nb + i;
-                if (n < P.N) {
+    // per image: sum the chunks' partial sums of squares in a fixed order (deterministic), then rescale
+    // the J columns this CTA wrote.
+    {
+        constexpr int CB = 64;                       // images per pass
+        constexpr int PARTS = TAIL_THREADS / CB;     // 8 chunk subsets
+        __shared__ float redc[PARTS][CB];
+        __shared__ float denom_s[CB];
+        for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+            const int j0 = chunk * P.jch;
+            const int J = min(P.jch, P.D_out - j0);
+            for (int n0 = 0; n0 < P.N; n0 += CB) {
+                const int nl = tid & (CB - 1), part = tid / CB;
+                float sacc = 0.0f;
+                if (n0 + nl < P.N)
+                    for (int ch = part; ch < P.n_chunks; ch += PARTS) sacc += __ldcg(P.partial + (size_t)ch * P.N + n0 + nl);
+                redc[part][nl] = sacc;
+                __syncthreads();
+                if (tid < CB) {
                     float tot = 0.0f;
-                    for (int ch = lane; ch < P.n_chunks; ch += 32) tot += __ldcg(P.partial + (size_t)ch * P.N + n);
-                    tot = warp_sum(tot);
-                    const float denom = sqrtf(tot) + P.eps_l2;
-                    if (lane < J) {
-                        float* o = P.out + (size_t)n * P.out_ld + j0 + lane;
-                        *o = *o / denom;
-                    }
+#pragma unroll
+                    for (int pp = 0; pp < PARTS; ++pp) tot += redc[pp][tid];
+                    denom_s[tid] = sqrtf(tot) + P.eps_l2;
                 }
+                __syncthreads();
+                const int cnt = min(CB, P.N - n0) * J;
+                for (int e = tid; e < cnt; e += TAIL_THREADS) {
+                    const int n = e / J, j = e - n * J;
+                    float* o = P.out + (size_t)(n0 + n) * P.out_ld + j0 + j;
+                    *o = __ldcg(o) / denom_s[n];
+                }
+                __syncthreads();
             }
         }
     }
+    stamp(P, 5);
 }
 
 // ---------------------------------------------------------------------- row L2N (A2)
@@ -389,7 +436,7 @@ using namespace cir;
 extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) {
     CIR_REQUIRE(bytes && N > 0 && C > 0 && D_out > 0, CIR_ERR_INVALID_ARG, "cir_tail_workspace_bytes: bad arguments");
     // pooled [N, C] + partial [D_out, N] (n_chunks <= D_out)
-    *bytes = align_up((size_t)N * C * 4, 256) + align_up((size_t)D_out * N * 4, 256);
+    *bytes = align_up((size_t)N * C * 4, 256) + align_up((size_t)D_out * N * 4, 256) + TAIL_STAMP_BYTES;
     return CIR_OK;
 }
 
@@ -430,6 +477,8 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
         P.pooled = static_cast<float*>(workspace);
         P.pooled_ld = C;
         P.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)N * C * 4, 256));
+        if (flags & CIR_TAIL_DEBUG_STAMPS)
+            P.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + need - TAIL_STAMP_BYTES);
     }
     if (whiten) {
         CIR_REQUIRE(Wt, CIR_ERR_INVALID_ARG, "cir_tail_fwd: whitening needs Wt");

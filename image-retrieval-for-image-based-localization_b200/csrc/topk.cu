@@ -59,35 +59,74 @@ struct SelParams {
     int32_t idx_offset;
 };
 
+constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
+
 template <int SRC>
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParams p) {
     __shared__ unsigned long long buf[SEL_N];
+    __shared__ int s_cnt[SEL_MAX_LISTS];      // list sizes of the current window of lists
+    __shared__ int s_off[SEL_MAX_LISTS + 1];  // exclusive prefix sums
     const int q = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int fill = 0;
-    int g = 0;
-    while (g < p.G) {
-        while (g < p.G) {
-            const int c = SRC == 0 ? __ldg(p.counts + (size_t)g * p.Qpad + q) : p.kin;
-            if (fill + c > SEL_N) break;
-            if (SRC == 0) {
-                const unsigned long long* L = p.lists + ((size_t)g * p.Qpad + q) * p.cap;
-                for (int t = tid; t < c; t += SEL_THREADS) buf[fill + t] = __ldcg(L + t);
-            } else {
-                const size_t o = ((size_t)g * p.Q + q) * p.kin;
-                for (int t = tid; t < c; t += SEL_THREADS) {
-                    const int32_t ix = __ldg(p.in_idx + o + t);
-                    buf[fill + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+    for (int g0 = 0; g0 < p.G;) {
+        // sizes of up to SEL_MAX_LISTS lists starting at g0, loaded in parallel
+        const int win = min(SEL_MAX_LISTS, p.G - g0);
+        for (int t = tid; t < win; t += SEL_THREADS)
+            s_cnt[t] = SRC == 0 ? __ldg(p.counts + (size_t)(g0 + t) * p.Qpad + q) : p.kin;
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan by one warp
+            int run = 0;
+            for (int base = 0; base < win; base += 32) {
+                const int c = base + lane < win ? s_cnt[base + lane] : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (base + lane < win) s_off[base + lane] = run + inc - c;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_off[win] = run;
+        }
+        __syncthreads();
+        int done = 0;     // lists of this window already consumed
+        while (done < win) {
+            // take as many lists as fit behind the `fill` survivors of the previous round
+            const int room = SEL_N - fill;
+            const int start = s_off[done];
+            int take = done;
+            while (take < win && s_off[take + 1] - start <= room) ++take;    // uniform across threads
+            // warp w copies lists done + w, done + w + 16, ...
+            for (int g = done + warp; g < take; g += SEL_THREADS / 32) {
+                const int c = s_cnt[g];
+                const int dst = fill + s_off[g] - start;
+                if (SRC == 0) {
+                    const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
+                    for (int t = lane; t < c; t += 32) buf[dst + t] = __ldcg(L + t);
+                } else {
+                    const size_t o = ((size_t)(g0 + g) * p.Q + q) * p.kin;
+                    for (int t = lane; t < c; t += 32) {
+                        const int32_t ix = __ldg(p.in_idx + o + t);
+                        buf[dst + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+                    }
                 }
             }
-            fill += c;
-            ++g;
+            fill += s_off[take] - start;
+            done = take;
+            const int P = next_pow2(fill);
+            for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
+            __syncthreads();
+            block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
+            if (fill > p.k) fill = p.k;
         }
-        const int P = next_pow2(fill);
-        for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
+        g0 += win;
         __syncthreads();
-        block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
-        if (fill > p.k) fill = p.k;
+    }
+    if (p.G == 0) {
+        for (int t = tid; t < p.k; t += SEL_THREADS) buf[t] = 0ull;
+        __syncthreads();
     }
     for (int t = tid; t < p.k; t += SEL_THREADS) {
         const unsigned long long key = t < fill ? buf[t] : 0ull;
@@ -95,6 +134,79 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
         p.out_scores[(size_t)q * p.out_ld + t] = ok ? key_score(key) : -INFINITY;
         p.out_idx[(size_t)q * p.out_ld + t] = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// k-th largest value of every row of a dense [Q, n] score block (n <= KTH_MAX_N): the warm
+// start tau0 of the fused top-k.  One block per row, row held in shared memory as ordered
+// u32, 4 x 8-bit radix-select passes with per-warp histograms.
+// ---------------------------------------------------------------------------------------
+constexpr int KTH_THREADS = 1024;
+
+__global__ void __launch_bounds__(KTH_THREADS)
+row_kth_largest_kernel(const float* __restrict__ scores, int n, long long ld, int k, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char kth_smem[];
+    uint32_t* vals = reinterpret_cast<uint32_t*>(kth_smem);                 // [n]
+    int* hist = reinterpret_cast<int*>(kth_smem + (size_t)n * 4);           // [32][256]
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_krem;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    if (n < k) {
+        if (tid == 0) out[q] = -INFINITY;
+        return;
+    }
+    const float* row = scores + (size_t)q * ld;
+    for (int t = tid; t < n; t += KTH_THREADS) vals[t] = float_to_ordered(__ldcs(row + t));
+    if (tid == 0) { s_prefix = 0u; s_krem = k; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int t = tid; t < 32 * 256; t += KTH_THREADS) hist[t] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int t = tid; t < n; t += KTH_THREADS) {
+            const uint32_t v = vals[t];
+            if ((v & himask) == prefix) atomicAdd(&hist[warp * 256 + ((v >> shift) & 255u)], 1);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int c = 0;
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) c += hist[w * 256 + tid];
+            hist[tid] = c;      // row 0 now holds the block histogram
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int krem = s_krem, b = 255;
+            for (; b > 0; --b) {
+                const int c = hist[b];
+                if (c >= krem) break;
+                krem -= c;
+            }
+            s_krem = krem;
+            s_prefix = prefix | ((uint32_t)b << shift);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[q] = ordered_to_float(s_prefix);
+}
+
+int launch_row_kth_largest(const float* scores, int Q, int n, long long ld, int k, float* out, cudaStream_t stream) {
+    const size_t smem = (size_t)n * 4 + 32 * 256 * 4;
+    const DeviceInfo& dev = device_info();
+    CIR_REQUIRE(n <= KTH_MAX_N && (int)smem + 1024 <= dev.max_smem_optin, CIR_ERR_UNSUPPORTED,
+                "row_kth_largest: n=%d too large for shared memory", n);
+    static thread_local int attr_dev = -1;
+    if (attr_dev != dev.device) {
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(row_kth_largest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            KTH_MAX_N * 4 + 32 * 256 * 4));
+        attr_dev = dev.device;
+    }
+    row_kth_largest_kernel<<<Q, KTH_THREADS, smem, stream>>>(scores, n, ld, k, out);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
 }
 
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,

@@ -43,9 +43,12 @@ extern "C" {
 /* flags of cir_tail_fwd */
 #define CIR_TAIL_NO_WHITEN 1u   /* globalHead.forward(x, do_whitening=False)            */
 #define CIR_TAIL_POOL_ONLY 2u   /* stop after pooling: GeM.forward alone (no L2N)       */
+#define CIR_TAIL_DEBUG_STAMPS 0x80000000u /* profiling aid: every CTA writes %globaltimer at its phase
+                                   boundaries into the last 64 KB of the workspace ([cta][8] u64) */
 
 /* flags of cir_search_topk */
-#define CIR_SEARCH_SORTED 0u    /* (default) lists sorted by (score desc, index asc)    */
+#define CIR_SEARCH_SORTED 0u      /* (default) lists sorted by (score desc, index asc)  */
+#define CIR_SEARCH_NO_PREPASS 1u  /* skip the threshold warm start (first-rows sample)   */
 
 const char* cir_last_error(void);
 int cir_version(void);

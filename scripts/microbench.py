@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Phase breakdown timings used while optimising (not part of the product)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "image-retrieval-for-image-based-localization_b200"))
+import torch
+from cirtorch_b200 import functional as LF, search as S
+dev = torch.device("cuda:0")
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("all", "tail"):
+    B, C, H, W = 64, 2048, 32, 32
+    xs = [torch.relu(torch.randn((B, C, H, W), device=dev)) for _ in range(2)]
+    Wt = torch.randn(2048, 2048, device=dev) * 0.01
+    b = torch.zeros(2048, device=dev)
+    p3 = torch.full((1,), 3.0, device=dev); p27 = torch.full((1,), 2.7, device=dev)
+    i = [0]
+    def nxt():
+        i[0] ^= 1; return xs[i[0]]
+    gb = B * C * H * W * 4 / 1e6
+    for name, fn in [
+        ("pool_only p=3", lambda: LF.descriptor_tail(nxt(), p=p3, pooling="GeM", pool_only=True)),
+        ("pool_only p=2.7", lambda: LF.descriptor_tail(nxt(), p=p27, pooling="GeM", pool_only=True)),
+        ("pool_only MAC", lambda: LF.descriptor_tail(nxt(), pooling="MAC", pool_only=True)),
+        ("no_whiten p=3", lambda: LF.descriptor_tail(nxt(), p=p3, pooling="GeM", do_whitening=False)),
+        ("full p=3", lambda: LF.descriptor_tail(nxt(), p=p3, weight=Wt, bias=b, pooling="GeM")),
+        ("full p=2.7", lambda: LF.descriptor_tail(nxt(), p=p27, weight=Wt, bias=b, pooling="GeM")),
+        ("torch clone (copy)", lambda: nxt().clone()),
+        ("torch sum (read)", lambda: nxt().sum()),
+    ]:
+        ms = timeit(fn)
+        print(f"tail {name:22s} {ms*1e3:8.1f} us  {gb/ms:8.1f} GB/s(x only)")
+if what in ("all", "tail", "stamps"):
+    import ctypes as C
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    B, Cc, H, W = 64, 2048, 32, 32
+    x = torch.relu(torch.randn((B, Cc, H, W), device=dev))
+    Wt = torch.randn(2048, 2048, device=dev) * 0.01
+    b = torch.zeros(2048, device=dev); p3 = torch.full((1,), 3.0, device=dev)
+    out = torch.empty((B, 2048), device=dev)
+    need = C.c_size_t(0); lib.cir_tail_workspace_bytes(B, Cc, 2048, C.byref(need))
+    ws = torch.zeros(need.value, dtype=torch.uint8, device=dev)
+    for it in range(3):
+        rc = lib.cir_tail_fwd(_lib.ptr(x), B, Cc, H, W, _lib.ptr(p3), 0, 1e-6, 1e-6, 0, _lib.ptr(Wt), _lib.ptr(b), 2048,
+                              _lib.ptr(out), 2048, _lib.ptr(ws), ws.numel(), 0x80000000, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+    st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :6].cpu().double()
+    t0 = st[:, 0].min()
+    names = ["start", "endA", "sync1", "endB", "sync2", "end"]
+    for j in range(6):
+        col = (st[:, j] - t0) / 1e3
+        print(f"stamp {names[j]:6s}: min {col.min():8.1f} us  mean {col.mean():8.1f}  max {col.max():8.1f}")
+if what in ("all", "search"):
+    N, D = 1_000_000, 2048
+    dbp = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+    rows = None
+    for a in range(0, N, 125_000):
+        blk = torch.randn((125_000, D), device=dev)
+        S.pack_rows(blk / blk.norm(dim=1, keepdim=True), "db", "bf16", out=dbp[a:a + 125_000])
+    for Q in (70, 128, 1024, 10_000):
+        q = torch.randn((Q, D), device=dev); q = q / q.norm(dim=1, keepdim=True)
+        qp = S.pack_rows(q, "query", "bf16")
+        s, i = S.search_packed(qp, dbp, 100)
+        tau = (s[:, -1] - 1e-4).contiguous()
+        n = 3 if Q > 2000 else 10
+        ms = timeit(lambda: S.search_packed(qp, dbp, 100), n=n)
+        ms_t = timeit(lambda: S.search_packed(qp, dbp, 100, tau0=tau), n=n)
+        s2, i2 = S.search_packed(qp, dbp, 100, tau0=tau)
+        print(f"search Q={Q:6d}: {ms:8.3f} ms ({2*Q*N*D/ms/1e9:7.1f} TF, {N*D*2/ms/1e6:7.1f} GB/s) | with exact tau0: {ms_t:8.3f} ms "
+              f"({2*Q*N*D/ms_t/1e9:7.1f} TF, {N*D*2/ms_t/1e6:7.1f} GB/s) same={bool(torch.equal(i, i2))}")
+    ms = timeit(lambda: dbp.sum(dtype=torch.float32), n=5)
+    print(f"torch sum over bf16 db: {ms:.3f} ms {N*D*2/ms/1e6:.1f} GB/s")

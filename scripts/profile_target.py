@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: runs a few launches of one hot kernel at its BASELINE.json size.
+    python scripts/profile_target.py tail|search10k|search70|mining [n_launches]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "image-retrieval-for-image-based-localization_b200"))
+import torch
+
+what = sys.argv[1]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+if what == "tail":
+    from bench import make_head, B, C, H, W
+    head = make_head(dev)
+    xs = [torch.relu(torch.randn((B, C, H, W), device=dev)) for _ in range(2)]
+    with torch.no_grad():
+        for i in range(n):
+            head(xs[i & 1])
+elif what in ("search10k", "search70"):
+    from cirtorch_b200 import search as S
+    N, D = 1_000_000, 2048
+    Q = 10_000 if what == "search10k" else 70
+    dbp = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+    for a in range(0, N, 125_000):
+        blk = torch.randn((125_000, D), device=dev)
+        S.pack_rows(blk / blk.norm(dim=1, keepdim=True), "db", "bf16", out=dbp[a:a + 125_000])
+    q = torch.randn((Q, D), device=dev)
+    qp = S.pack_rows(q / q.norm(dim=1, keepdim=True), "query", "bf16")
+    for i in range(n):
+        S.search_packed(qp, dbp, 100)
+elif what == "mining":
+    from cirtorch_b200.mining import mine_hard_negatives_rows
+    q = torch.randn((2000, 2048), device=dev)
+    p = torch.randn((20000, 2048), device=dev)
+    q, p = q / q.norm(dim=1, keepdim=True), p / p.norm(dim=1, keepdim=True)
+    qc = torch.randint(0, 700, (2000,), device=dev, dtype=torch.int32)
+    pc = torch.randint(0, 700, (20000,), device=dev, dtype=torch.int32)
+    for i in range(n):
+        mine_hard_negatives_rows(q, p, qc, pc, 5)
+torch.cuda.synchronize()
+print("ok", what)
