@@ -2,32 +2,48 @@
 //
 // Replaces cirtorch/modules/pools.py:37-38, normalizations.py:15-16 and
 // heads/global_head.py:52-67 (seven eager PyTorch ops, three full passes over the map)
-// with ONE cooperative launch:
-//   phase A  every warp streams (n, c) rows of the NCHW map with 128-bit no-allocate
-//            loads, two rows (8 KB) in flight per warp, clamp + x^p + shuffle reduce ->
-//            pooled[n, c] (N*C floats, stays in L2).  This is the HBM-bound part.
+// with ONE cooperative launch of one 512-thread CTA per SM:
+//   phase A  the HBM stream.  Warp 15 is a producer: one thread feeds a ring of 16 KB
+//            shared-memory slots with cp.async.bulk (TMA bulk copies of whole (n, c) rows,
+//            L2 evict-first) completing on mbarriers; warps 0..14 consume rows from shared
+//            memory (clamp, x^p, sum / max; warp-shuffle reduce) and finish 32 rows at a
+//            time (mean^(1/p)) -> pooled[n, c] (N*C floats, stays in L2).  The bytes in
+//            flight are the ring, not registers.  Meanwhile the CTA's slice of W (<= 16
+//            output rows, <= 128 KB) is prefetched into shared memory with cp.async.
+//            Rows that TMA cannot move (H*W % 4 != 0, > 16 KB, unaligned) take a direct-load path.
 //   barrier  cooperative grid sync
-//   phase B  CTA i owns a slice of <= 16 output dims; its W slice (<= 128 KB) was
-//            prefetched into shared memory with cp.async while phase A ran.  Each warp
-//            takes 4 images, lanes split K, exact fp32 FMA, shuffle reduce.  The first
-//            L2N is folded in as a scale of the accumulators.
+//   phase B  CTA i owns a slice of <= 16 output dims.  Y[64 x 16] = G[64 x K] . Wslice^T on
+//            mma.sync m16n8k16 bf16 with every fp32 operand split into hi + lo bf16
+//            (hi.hi + hi.lo + lo.hi, fp32 accumulate: ~1e-5 relative, inside the 1e-4 bar).
+//            16 warps = 2 image halves x 8 K ranges; A fragments are loaded straight from the
+//            L2-resident pooled vectors (one full 128 B line per 4 lanes, next block
+//            prefetched), B fragments from the shared-memory W slice; a shared-memory
+//            reduction over the K ranges; the first L2N is folded in as a scale.
 //   barrier  cooperative grid sync (per-chunk partial sums of squares)
-//   phase C  every thread rescales the outputs it wrote: second L2N.
+//   phase C  second L2N: partial sums added in a fixed order (deterministic), outputs rescaled.
 //
 // Algorithmic HBM bytes per launch: N*C*H*W*4 (x) + D_out*C*4 (W) + D_out*4 (b) + N*D_out*4 (out).
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
 namespace cir {
 
+using namespace ptx;
+
 constexpr int TAIL_THREADS = 512;
 constexpr int TAIL_WARPS = TAIL_THREADS / 32;
-constexpr int TAIL_JMAX = 16;    // output dims per phase-B chunk
-constexpr int TAIL_KC = 2048;    // K extent of the W slice staged in shared memory
-constexpr int TAIL_IMG = 4;      // images per warp in phase B
-constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;   // debug time stamps: up to 1024 CTAs x 8 slots
+constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 consume, warp 15 produces
+constexpr int TAIL_JMAX = 16;                        // output dims per phase-B chunk (two n8 MMA tiles)
+constexpr int TAIL_KC = 2048;                        // K extent of the W slice staged in shared memory
+constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows, <= 16 KB
+constexpr int TAIL_MAX_SLOTS = 8;
+constexpr int TAIL_MB = 64;                          // images per phase-B pass
+constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;    // debug time stamps: up to 1024 CTAs x 8 slots
+// phase-B reduction scratch (aliases the ring): [8 K ranges][8 tile combos][32 lanes][4] + [8][64] + [64][16] + [64]
+constexpr int TAIL_RED_FLOATS = 8 * 8 * 32 * 4 + 8 * TAIL_MB + TAIL_MB * TAIL_JMAX + TAIL_MB;
 
 struct TailParams {
     const float* x;
@@ -46,16 +62,15 @@ struct TailParams {
     float* partial;    // [n_chunks, N] sums of squares of the un-normalised outputs
     int jch, n_chunks;
     unsigned flags;
+    int bulk_ok;       // rows can be moved by cp.async.bulk
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
+    int n_slots;       // ring slots
+    int w_bytes;       // shared-memory bytes reserved for the W slice
     unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
 };
 
 __device__ __forceinline__ void stamp(const TailParams& P, int slot) {
-    if (P.stamps && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.stamps[(size_t)blockIdx.x * 8 + slot] = t;
-    }
+    if (P.stamps && threadIdx.x == 0) P.stamps[(size_t)blockIdx.x * 8 + slot] = global_timer_ns();
 }
 
 __device__ __forceinline__ float fast_lg2(float x) {
@@ -73,22 +88,16 @@ __device__ __forceinline__ float fast_ex2(float x) {
 enum { PM_GENERAL = 0, PM_1 = 1, PM_2 = 2, PM_3 = 3, PM_4 = 4, PM_MAX = 5, PM_MEAN = 6 };
 
 template <int PM>
-__device__ __forceinline__ float term(float v, float eps, float p) {
-    if (PM == PM_MAX || PM == PM_MEAN) return v;
-    float t = fmaxf(v, eps);
-    if (PM == PM_1) return t;
-    if (PM == PM_2) return t * t;
-    if (PM == PM_3) return t * t * t;
-    if (PM == PM_4) { float t2 = t * t; return t2 * t2; }
-    return fast_ex2(p * fast_lg2(t));
-}
-
-template <int PM>
 __device__ __forceinline__ float fold(float acc, float v, float eps, float p) {
     if (PM == PM_MAX) return fmaxf(acc, v);
-    return acc + term<PM>(v, eps, p);
+    if (PM == PM_MEAN) return acc + v;
+    const float t = fmaxf(v, eps);
+    if (PM == PM_1) return acc + t;
+    if (PM == PM_2) return fmaf(t, t, acc);
+    if (PM == PM_3) return fmaf(t * t, t, acc);
+    if (PM == PM_4) { const float t2 = t * t; return fmaf(t2, t2, acc); }
+    return acc + fast_ex2(p * fast_lg2(t));
 }
-
 template <int PM>
 __device__ __forceinline__ float fold4(float acc, const float4& v, float eps, float p) {
     acc = fold<PM>(acc, v.x, eps, p);
@@ -108,66 +117,103 @@ __device__ __forceinline__ int classify_p(int pool_mode, float p) {
     return PM_GENERAL;
 }
 
-// warp-uniform dispatch of one row's 8 preloaded vectors
-__device__ __forceinline__ float fold_row8(int pm, const float4 (&v)[8], const bool (&ok)[8],
-                                           float acc, float eps, float p) {
-#define CIR_FOLD_CASE(PMV)                                                     \
-    case PMV: {                                                                \
-        _Pragma("unroll") for (int j = 0; j < 8; ++j)                          \
-            if (ok[j]) acc = fold4<PMV>(acc, v[j], eps, p);                    \
-        break;                                                                 \
-    }
-    switch (pm) {
-        CIR_FOLD_CASE(PM_3)
-        CIR_FOLD_CASE(PM_2)
-        CIR_FOLD_CASE(PM_1)
-        CIR_FOLD_CASE(PM_4)
-        CIR_FOLD_CASE(PM_MAX)
-        CIR_FOLD_CASE(PM_MEAN)
-        default: {
+// per-lane partial of one row held as float4s (shared or global memory), lanes stride the vectors
+template <int PM, bool GLOBAL>
+__device__ __forceinline__ float row_partial_vec(const float4* v, int nvec, int lane, float eps, float p) {
+    float a0 = PM == PM_MAX ? -INFINITY : 0.0f, a1 = a0;
+    int i = lane;
+    for (; i + 32 * 7 < nvec; i += 256) {
+        float4 u[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (ok[j]) acc = fold4<PM_GENERAL>(acc, v[j], eps, p);
+        for (int j = 0; j < 8; ++j) u[j] = GLOBAL ? ld_stream_f4(v + i + 32 * j) : v[i + 32 * j];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            a0 = fold4<PM>(a0, u[j], eps, p);
+            a1 = fold4<PM>(a1, u[j + 1], eps, p);
         }
     }
-#undef CIR_FOLD_CASE
-    return acc;
+    for (; i < nvec; i += 32) a0 = fold4<PM>(a0, GLOBAL ? ld_stream_f4(v + i) : v[i], eps, p);
+    return PM == PM_MAX ? fmaxf(a0, a1) : a0 + a1;
+}
+template <int PM>
+__device__ __forceinline__ float row_partial_scalar(const float* x, int n, int lane, float eps, float p) {
+    float a = PM == PM_MAX ? -INFINITY : 0.0f;
+    for (int i = lane; i < n; i += 32) a = fold<PM>(a, ld_stream_f1(x + i), eps, p);
+    return a;
 }
 
-__device__ __forceinline__ float fold_scalar(int pm, float acc, float v, float eps, float p) {
+// warp-uniform dispatch on the exponent class; returns the warp-reduced row statistic in every lane
+template <bool GLOBAL>
+__device__ __forceinline__ float row_reduce(int pm, const float* row, int HW, bool vec, int lane, float eps, float p) {
+    float a;
+#define CIR_ROW_CASE(PMV)                                                                               \
+    case PMV:                                                                                           \
+        a = vec ? row_partial_vec<PMV, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p) \
+                : row_partial_scalar<PMV>(row, HW, lane, eps, p);                                       \
+        break;
     switch (pm) {
-        case PM_3: return fold<PM_3>(acc, v, eps, p);
-        case PM_2: return fold<PM_2>(acc, v, eps, p);
-        case PM_1: return fold<PM_1>(acc, v, eps, p);
-        case PM_4: return fold<PM_4>(acc, v, eps, p);
-        case PM_MAX: return fold<PM_MAX>(acc, v, eps, p);
-        case PM_MEAN: return fold<PM_MEAN>(acc, v, eps, p);
-        default: return fold<PM_GENERAL>(acc, v, eps, p);
+        CIR_ROW_CASE(PM_3)
+        CIR_ROW_CASE(PM_2)
+        CIR_ROW_CASE(PM_1)
+        CIR_ROW_CASE(PM_4)
+        CIR_ROW_CASE(PM_MAX)
+        CIR_ROW_CASE(PM_MEAN)
+        default:
+            a = vec ? row_partial_vec<PM_GENERAL, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p)
+                    : row_partial_scalar<PM_GENERAL>(row, HW, lane, eps, p);
     }
+#undef CIR_ROW_CASE
+    return pm == PM_MAX ? warp_max(a) : warp_sum(a);
 }
 
 __device__ __forceinline__ float finish_row(int pm, float acc, int HW, float p) {
-    // acc already reduced over the warp
     if (pm == PM_MAX) return acc;
-    float mean = acc / (float)HW;
+    const float mean = acc / (float)HW;
     if (pm == PM_MEAN || pm == PM_1) return mean;
     // reference: .pow(1. / self.p) with the reciprocal rounded to fp32 (pools.py:38)
     return powf(mean, 1.0f / p);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-    return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+// TMA bulk copy global -> shared (1-D, size % 16 == 0), completes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                          uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams P) {
-    extern __shared__ __align__(16) float Ws[];   // [TAIL_JMAX][TAIL_KC] (phase B only)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float hi_k) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo_k, hi_k);     // .x (low half) = lower k index
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// split two fp32 values into packed bf16 hi parts and packed bf16 residuals
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = pack_bf16x2(a - __low2float(h), b - __high2float(h));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailParams P) {
+    extern __shared__ __align__(128) unsigned char tail_smem[];
+    float* Ws = reinterpret_cast<float*>(tail_smem);                               // [jch][TAIL_KC]
+    unsigned char* ring = tail_smem + P.w_bytes;                                   // [n_slots][16 KB]
+    float* red = reinterpret_cast<float*>(ring);                                   // phase B scratch (aliases the ring)
+    __shared__ __align__(8) uint64_t full_bar[TAIL_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t empty_bar[TAIL_MAX_SLOTS];
     cg::grid_group grid = cg::this_grid();
 
     const int tid = threadIdx.x;
@@ -199,58 +245,86 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
     // ------------------------------------------------------------------ phase A
     {
         const long long rows = (long long)P.N * P.C;
-        const long long pairs = (rows + 1) >> 1;
-        const long long gw = (long long)blockIdx.x * TAIL_WARPS + warp;
-        const long long nw = (long long)gridDim.x * TAIL_WARPS;
+        const long long r0 = rows * blockIdx.x / gridDim.x, r1 = rows * (blockIdx.x + 1) / gridDim.x;
+        const int my_rows = (int)(r1 - r0);
         const int HW = P.HW;
-        for (long long pr = gw; pr < pairs; pr += nw) {
-            const long long r0 = pr * 2, r1 = r0 + 1;
-            const bool has1 = r1 < rows;
-            const int c0 = (int)(r0 % P.C), c1 = (int)(r1 % P.C);
-            const float p0 = P.pool_mode == CIR_POOL_GEM ? __ldg(P.p + c0 * P.p_stride) : 1.0f;
-            const float p1 = (P.pool_mode == CIR_POOL_GEM && has1) ? __ldg(P.p + c1 * P.p_stride) : p0;
-            const int pm0 = classify_p(P.pool_mode, p0), pm1 = classify_p(P.pool_mode, p1);
-            float a0 = pm0 == PM_MAX ? -INFINITY : 0.0f;
-            float a1 = a0;
-            const float* x0 = P.x + r0 * HW;
-            const float* x1 = P.x + (has1 ? r1 : r0) * HW;
-            if (P.vec_ok) {
-                const int nvec = HW >> 2;
-                const float4* v0 = reinterpret_cast<const float4*>(x0);
-                const float4* v1 = reinterpret_cast<const float4*>(x1);
-                for (int base = 0; base < nvec; base += 256) {
-                    float4 u0[8], u1[8];
-                    bool ok[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = base + j * 32 + lane;
-                        ok[j] = i < nvec;
-                        if (ok[j]) u0[j] = ld_stream_f4(v0 + i);
+        const bool gem = P.pool_mode == CIR_POOL_GEM;
+
+        // lane l of a consumer warp parks the statistic of the l-th row of the current batch of 32
+        float held = 0.0f;
+        long long held_row = -1;
+        int nheld = 0;
+        auto flush = [&]() {
+            if (held_row >= 0) {
+                const int c = (int)(held_row % P.C);
+                const long long n = held_row / P.C;
+                const float pl = gem ? __ldg(P.p + c * P.p_stride) : 1.0f;
+                P.pooled[n * P.pooled_ld + c] = finish_row(classify_p(P.pool_mode, pl), held, HW, pl);
+            }
+            held_row = -1;
+        };
+        auto take = [&](float a, long long row) {
+            if (lane == (nheld & 31)) { held = a; held_row = row; }
+            if ((++nheld & 31) == 0) flush();
+        };
+
+        if (P.bulk_ok) {
+            const int rps = max(1, TAIL_SLOT_BYTES / (HW * 4));            // rows per slot
+            const int iters = (my_rows + rps - 1) / rps;
+            if (tid == 0) {
+                for (int s = 0; s < P.n_slots; ++s) {
+                    mbar_init(&full_bar[s], 1);
+                    mbar_init(&empty_bar[s], TAIL_CONSUMERS);
+                }
+                fence_barrier_init();
+            }
+            __syncthreads();
+            if (warp == TAIL_CONSUMERS) {
+                if (lane == 0) {
+                    const uint64_t pol = policy_evict_first();
+                    int slot = 0;
+                    uint32_t phase = 0;
+                    for (int t = 0; t < iters; ++t) {
+                        mbar_wait(&empty_bar[slot], phase ^ 1u);
+                        const int nr = min(rps, my_rows - t * rps);
+                        const uint32_t bytes = (uint32_t)nr * (uint32_t)HW * 4u;
+                        mbar_arrive_expect_tx(&full_bar[slot], bytes);
+                        bulk_load(ring + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
+                                  &full_bar[slot], pol);
+                        if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = base + j * 32 + lane;
-                        if (ok[j]) u1[j] = ld_stream_f4(v1 + i);
-                    }
-                    a0 = fold_row8(pm0, u0, ok, a0, P.eps_gem, p0);
-                    a1 = fold_row8(pm1, u1, ok, a1, P.eps_gem, p1);
                 }
             } else {
-                for (int i = lane; i < HW; i += 32) {
-                    a0 = fold_scalar(pm0, a0, ld_stream_f1(x0 + i), P.eps_gem, p0);
-                    a1 = fold_scalar(pm1, a1, ld_stream_f1(x1 + i), P.eps_gem, p1);
+                int slot = 0;
+                uint32_t phase = 0;
+                // the exponent class is warp-uniform per row; with a shared p it is constant
+                for (int t = 0; t < iters; ++t) {
+                    mbar_wait(&full_bar[slot], phase);
+                    const int nr = min(rps, my_rows - t * rps);
+                    const int base = t * rps;
+                    int j = (warp - base % TAIL_CONSUMERS + TAIL_CONSUMERS) % TAIL_CONSUMERS;   // first local row with (base + j) % 15 == warp
+                    for (; j < nr; j += TAIL_CONSUMERS) {
+                        const long long row = r0 + base + j;
+                        const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
+                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
+                        const float a = row_reduce<false>(classify_p(P.pool_mode, pr), src, HW, true, lane, P.eps_gem, pr);
+                        take(a, row);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[slot]);
+                    if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
                 }
+                flush();
             }
-            a0 = pm0 == PM_MAX ? warp_max(a0) : warp_sum(a0);
-            a1 = pm1 == PM_MAX ? warp_max(a1) : warp_sum(a1);
-            if (lane == 0) {
-                const long long n0 = r0 / P.C;
-                P.pooled[n0 * P.pooled_ld + c0] = finish_row(pm0, a0, HW, p0);
-                if (has1) {
-                    const long long n1 = r1 / P.C;
-                    P.pooled[n1 * P.pooled_ld + c1] = finish_row(pm1, a1, HW, p1);
-                }
+        } else {
+            // direct loads: every warp takes rows r0 + warp, r0 + warp + 16, ...
+            for (int j = warp; j < my_rows; j += TAIL_WARPS) {
+                const long long row = r0 + j;
+                const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
+                const float a = row_reduce<true>(classify_p(P.pool_mode, pr), P.x + row * HW, HW, P.vec_ok != 0, lane, P.eps_gem, pr);
+                take(a, row);
             }
+            flush();
         }
     }
     stamp(P, 1);
@@ -261,18 +335,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
 
     // ------------------------------------------------------------------ no whitening
     if (!whiten) {
-        __shared__ float red[TAIL_WARPS];
+        __shared__ float redn[TAIL_WARPS];
         for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
             const float* g = P.pooled + (size_t)n * P.pooled_ld;
             float ss = 0.0f;
             for (int c = tid; c < P.C; c += TAIL_THREADS) { float v = __ldcg(g + c); ss += v * v; }
             ss = warp_sum(ss);
             __syncthreads();
-            if (lane == 0) red[warp] = ss;
+            if (lane == 0) redn[warp] = ss;
             __syncthreads();
             float tot = 0.0f;
 #pragma unroll
-            for (int w = 0; w < TAIL_WARPS; ++w) tot += red[w];
+            for (int w = 0; w < TAIL_WARPS; ++w) tot += redn[w];
             const float denom = sqrtf(tot) + P.eps_l2;
             for (int c = tid; c < P.C; c += TAIL_THREADS)
                 P.out[(size_t)n * P.out_ld + c] = __ldcg(g + c) / denom;
@@ -281,90 +355,178 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(TailParams 
     }
 
     // ------------------------------------------------------------------ phase B
-    // Every CTA reads all pooled vectors from L2; CTAs start at different K offsets so that they do not
-    // all hit the same L2 lines at the same moment, and each lane prefetches its next 4 x float4 while it
-    // multiplies the current ones.
-    for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-        const int j0 = chunk * P.jch;
-        const int J = min(P.jch, P.D_out - j0);
-        for (int n0 = 0; n0 < P.N; n0 += TAIL_WARPS * TAIL_IMG) {
-            const int nb = n0 + warp * TAIL_IMG;
-            float acc[TAIL_IMG][TAIL_JMAX];
-            float ss[TAIL_IMG];
+    {
+        float* red_acc = red;                               // [8 wk][8 combo][32 lanes][4]
+        float* red_ss = red_acc + 8 * 8 * 32 * 4;           // [8 wk][64]
+        float* ysq = red_ss + 8 * TAIL_MB;                  // [64][16]
+        float* inv_s = ysq + TAIL_MB * TAIL_JMAX;           // [64]
+        const int g = lane >> 2, tig = lane & 3;
+        const int wm = warp & 1, wk = warp >> 1;            // image half, K range
+        for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+            const int j0 = chunk * P.jch;
+            const int J = min(P.jch, P.D_out - j0);
+            for (int n0 = 0; n0 < P.N; n0 += TAIL_MB) {
+                float acc[2][2][4];
+                float ss[2][2];
 #pragma unroll
-            for (int i = 0; i < TAIL_IMG; ++i) {
-                ss[i] = 0.0f;
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int j = 0; j < TAIL_JMAX; ++j) acc[i][j] = 0.0f;
-            }
-            for (int kc0 = 0; kc0 < P.C; kc0 += TAIL_KC) {
-                if (staged_chunk != chunk || staged_kc0 != kc0) {
-                    __syncthreads();      // everyone is done with the previous tile
-                    stage_W(chunk, kc0);
-                    staged_chunk = chunk;
-                    staged_kc0 = kc0;
-                }
-                cp_async_wait_all();
-                __syncthreads();
-                const int kw = min(TAIL_KC, P.C - kc0);
-                const int iters = (kw + 127) >> 7;
-                if (nb < P.N) {
-                    const float* gbase = P.pooled + (size_t)nb * P.pooled_ld + kc0 + lane * 4;
-                    auto load_g = [&](int it, float4 (&g)[TAIL_IMG]) {
-                        const int k = it * 128 + lane * 4;
+                    for (int x2 = 0; x2 < 2; ++x2) {
+                        ss[mt][x2] = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < TAIL_IMG; ++i) {
-                            g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (k < kw && nb + i < P.N)
-                                g[i] = __ldcg(reinterpret_cast<const float4*>(gbase + (size_t)i * P.pooled_ld + it * 128));
+                        for (int r = 0; r < 4; ++r) acc[mt][x2][r] = 0.0f;
+                    }
+                for (int kc0 = 0; kc0 < P.C; kc0 += TAIL_KC) {
+                    if (staged_chunk != chunk || staged_kc0 != kc0) {
+                        __syncthreads();      // everyone is done with the previous tile
+                        stage_W(chunk, kc0);
+                        staged_chunk = chunk;
+                        staged_kc0 = kc0;
+                    }
+                    cp_async_wait_all();
+                    __syncthreads();
+                    const int kw = min(TAIL_KC, P.C - kc0);
+                    // this warp's K range inside the tile, in blocks of 32
+                    const int kr0 = wk * (TAIL_KC / 8);
+                    const int nblk = max(0, min(TAIL_KC / 8, kw - kr0) + 31) >> 5;
+                    // rows (images) of the 4 fragment row slots: [mt][rsel]
+                    const float* arow[2][2];
+                    bool aok[2][2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int rs = 0; rs < 2; ++rs) {
+                            const int n = n0 + wm * 32 + mt * 16 + g + rs * 8;
+                            aok[mt][rs] = n < P.N;
+                            arow[mt][rs] = P.pooled + (size_t)(aok[mt][rs] ? n : 0) * P.pooled_ld + kc0 + kr0 + tig * 8;
                         }
+                    auto load_a = [&](int blk, float4 (&a)[2][2][2]) {
+                        const int kk = kr0 + blk * 32 + tig * 8;
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int rs = 0; rs < 2; ++rs)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    a[mt][rs][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (aok[mt][rs] && kk + h * 4 < kw)
+                                        a[mt][rs][h] = __ldcg(reinterpret_cast<const float4*>(arow[mt][rs] + blk * 32 + h * 4));
+                                }
                     };
-                    int it = (int)(blockIdx.x % (unsigned)iters);
-                    float4 g_next[TAIL_IMG];
-                    load_g(it, g_next);
-                    for (int t = 0; t < iters; ++t) {
-                        float4 g[TAIL_IMG];
+                    // CTAs start at different blocks so that they do not hit the same L2 lines at the same moment
+                    int blk = nblk > 0 ? (int)(blockIdx.x % (unsigned)nblk) : 0;
+                    float4 a_next[2][2][2];
+                    if (nblk > 0) load_a(blk, a_next);
+                    for (int t = 0; t < nblk; ++t) {
+                        float4 a[2][2][2];
 #pragma unroll
-                        for (int i = 0; i < TAIL_IMG; ++i) g[i] = g_next[i];
-                        const int k = it * 128 + lane * 4;
-                        if (++it == iters) it = 0;
-                        if (t + 1 < iters) load_g(it, g_next);
-                        if (k < kw) {
+                        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                            for (int i = 0; i < TAIL_IMG; ++i) ss[i] += dot4(g[i], g[i]);
+                            for (int rs = 0; rs < 2; ++rs)
 #pragma unroll
-                            for (int j = 0; j < TAIL_JMAX; ++j) {
-                                if (j < J) {
-                                    const float4 w = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + k]);
+                                for (int h = 0; h < 2; ++h) a[mt][rs][h] = a_next[mt][rs][h];
+                        const int kk = kr0 + blk * 32 + tig * 8;
+                        if (++blk == nblk) blk = 0;
+                        if (t + 1 < nblk) load_a(blk, a_next);
+                        // B fragments of the two 8-dim tiles: W rows j = nt*8 + g, the same 8 consecutive k as A
+                        uint32_t bhi[2][2][2], blo[2][2][2];     // [nt][kstep][reg]
 #pragma unroll
-                                    for (int i = 0; i < TAIL_IMG; ++i) acc[i][j] += dot4(w, g[i]);
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int j = nt * 8 + g;
+                            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+                            if (j < J && kk < kw) w0 = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + kk]);
+                            if (j < J && kk + 4 < kw) w1 = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + kk + 4]);
+                            split2(w0.x, w0.y, bhi[nt][0][0], blo[nt][0][0]);
+                            split2(w0.z, w0.w, bhi[nt][0][1], blo[nt][0][1]);
+                            split2(w1.x, w1.y, bhi[nt][1][0], blo[nt][1][0]);
+                            split2(w1.z, w1.w, bhi[nt][1][1], blo[nt][1][1]);
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+                            for (int rs = 0; rs < 2; ++rs) {
+                                const float4 u = a[mt][rs][0], v = a[mt][rs][1];
+                                ss[mt][rs] += (u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w) + (v.x * v.x + v.y * v.y) +
+                                              (v.z * v.z + v.w * v.w);
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                // k step ks uses the floats 4*ks .. 4*ks+3 of the lane's 8: slots (2 tig, 2 tig + 1) and (+8, +9)
+                                const float4 r0v = a[mt][0][ks], r1v = a[mt][1][ks];
+                                uint32_t ahi[4], alo[4];
+                                split2(r0v.x, r0v.y, ahi[0], alo[0]);
+                                split2(r1v.x, r1v.y, ahi[1], alo[1]);
+                                split2(r0v.z, r0v.w, ahi[2], alo[2]);
+                                split2(r1v.z, r1v.w, ahi[3], alo[3]);
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) {
+                                    mma_bf16_16816(acc[mt][nt], ahi, bhi[nt][ks]);
+                                    mma_bf16_16816(acc[mt][nt], ahi, blo[nt][ks]);
+                                    mma_bf16_16816(acc[mt][nt], alo, bhi[nt][ks]);
                                 }
                             }
                         }
                     }
                 }
-            }
-            if (nb < P.N) {
+                // ---- reduce the 8 K ranges through shared memory
+                __syncthreads();   // the ring / previous pass scratch is free
 #pragma unroll
-                for (int i = 0; i < TAIL_IMG; ++i) {
-                    ss[i] = warp_sum(ss[i]);
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int j = 0; j < TAIL_JMAX; ++j) acc[i][j] = warp_sum(acc[i][j]);
-                }
-                const float bj = (lane < J && P.bias) ? __ldg(P.bias + j0 + lane) : 0.0f;
-#pragma unroll
-                for (int i = 0; i < TAIL_IMG; ++i) {
-                    if (nb + i < P.N) {
-                        // first L2N folded in: W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
-                        const float inv = 1.0f / (sqrtf(ss[i]) + P.eps_l2);
-                        float y = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < TAIL_JMAX; ++j)
-                            if (lane == j) y = acc[i][j] * inv + bj;
-                        if (lane < J) P.out[(size_t)(nb + i) * P.out_ld + j0 + lane] = y;
-                        const float sq = warp_sum(lane < J ? y * y : 0.0f);
-                        if (lane == 0) P.partial[(size_t)chunk * P.N + nb + i] = sq;
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int combo = (wm * 2 + mt) * 2 + nt;
+                        *reinterpret_cast<float4*>(&red_acc[((wk * 8 + combo) * 32 + lane) * 4]) =
+                            make_float4(acc[mt][nt][0], acc[mt][nt][1], acc[mt][nt][2], acc[mt][nt][3]);
                     }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) {
+                        float s = ss[mt][rs];
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        if (tig == 0) red_ss[wk * TAIL_MB + wm * 32 + mt * 16 + g + rs * 8] = s;
+                    }
+                __syncthreads();
+                if (tid < TAIL_MB) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) s += red_ss[k8 * TAIL_MB + tid];
+                    inv_s[tid] = 1.0f / (sqrtf(s) + P.eps_l2);      // first L2N: W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
+                }
+                __syncthreads();
+                {
+                    // thread (warp, lane): tile combo = warp & 7, fragment row half = warp >> 3
+                    const int combo = warp & 7, rp = warp >> 3;
+                    const int cwm = combo >> 2, cmt = (combo >> 1) & 1, cnt = combo & 1;
+                    float y0 = 0.0f, y1 = 0.0f;
+#pragma unroll
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const float2 v = *reinterpret_cast<const float2*>(&red_acc[((k8 * 8 + combo) * 32 + lane) * 4 + rp * 2]);
+                        y0 += v.x;
+                        y1 += v.y;
+                    }
+                    const int nl = cwm * 32 + cmt * 16 + g + rp * 8;
+                    const int jl = cnt * 8 + tig * 2;
+                    const int n = n0 + nl;
+                    const float inv = inv_s[nl];
+                    y0 = y0 * inv + ((jl < J && P.bias) ? __ldg(P.bias + j0 + jl) : 0.0f);
+                    y1 = y1 * inv + ((jl + 1 < J && P.bias) ? __ldg(P.bias + j0 + jl + 1) : 0.0f);
+                    if (jl >= J) y0 = 0.0f;
+                    if (jl + 1 >= J) y1 = 0.0f;
+                    if (n < P.N) {
+                        if (jl < J) P.out[(size_t)n * P.out_ld + j0 + jl] = y0;
+                        if (jl + 1 < J) P.out[(size_t)n * P.out_ld + j0 + jl + 1] = y1;
+                    }
+                    ysq[nl * TAIL_JMAX + jl] = y0 * y0;
+                    ysq[nl * TAIL_JMAX + jl + 1] = y1 * y1;
+                }
+                __syncthreads();
+                if (tid < TAIL_MB && n0 + tid < P.N) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < TAIL_JMAX; ++j) s += ysq[tid * TAIL_JMAX + j];
+                    P.partial[(size_t)chunk * P.N + n0 + tid] = s;
                 }
             }
         }
@@ -435,7 +597,7 @@ using namespace cir;
 
 extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) {
     CIR_REQUIRE(bytes && N > 0 && C > 0 && D_out > 0, CIR_ERR_INVALID_ARG, "cir_tail_workspace_bytes: bad arguments");
-    // pooled [N, C] + partial [D_out, N] (n_chunks <= D_out)
+    // pooled [N, C] + partial [D_out, N] (n_chunks <= D_out) + debug stamps
     *bytes = align_up((size_t)N * C * 4, 256) + align_up((size_t)D_out * N * 4, 256) + TAIL_STAMP_BYTES;
     return CIR_OK;
 }
@@ -462,9 +624,9 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.p = p; P.p_stride = p_stride; P.eps_gem = eps_gem; P.eps_l2 = eps_l2; P.pool_mode = pool_mode;
     P.Wt = Wt; P.bias = bias; P.D_out = D_out; P.out = out; P.out_ld = out_ld; P.flags = flags;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
 
     const int grid = dev.num_sms;
-    size_t smem = 0;
     if (pool_only) {
         P.pooled = out; P.pooled_ld = out_ld;
     } else {
@@ -488,19 +650,26 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
         if (jch > TAIL_JMAX) jch = TAIL_JMAX;
         P.jch = jch;
         P.n_chunks = (D_out + jch - 1) / jch;
-        smem = (size_t)TAIL_JMAX * TAIL_KC * sizeof(float);
-        CIR_REQUIRE((int)smem <= dev.max_smem_optin, CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
+        P.w_bytes = (int)align_up((size_t)jch * TAIL_KC * sizeof(float), 1024);
     }
+    // ring: as many 16 KB slots as fit beside the W slice (and at least the phase-B scratch)
+    const int static_smem = 4096;     // barriers + phase-C arrays, with slack
+    int slots = (dev.max_smem_optin - static_smem - P.w_bytes) / TAIL_SLOT_BYTES;
+    if (slots > TAIL_MAX_SLOTS) slots = TAIL_MAX_SLOTS;
+    const int min_slots = (int)((TAIL_RED_FLOATS * sizeof(float) + TAIL_SLOT_BYTES - 1) / TAIL_SLOT_BYTES);
+    CIR_REQUIRE(slots >= (whiten ? min_slots : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
+    P.n_slots = slots;
+    const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES;
     static thread_local int attr_set_dev = -1;
     if (attr_set_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            TAIL_JMAX * TAIL_KC * (int)sizeof(float)));
+                                            dev.max_smem_optin - static_smem));
         attr_set_dev = dev.device;
     }
     void* args[] = {&P};
     if (pool_only) {
         // no grid barrier on this path: a plain launch is enough
-        tail_fused_kernel<<<grid, TAIL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(P);
+        tail_fused_kernel<<<grid, TAIL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(P);
         CIR_CHECK_CUDA(cudaGetLastError());
     } else {
         CIR_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)tail_fused_kernel, dim3(grid), dim3(TAIL_THREADS),
