@@ -82,11 +82,19 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 __device__ __forceinline__ unsigned long long make_key(float s, uint32_t idx) {
     return ((unsigned long long)float_to_ordered(s) << 32) | (unsigned long long)(0xffffffffu - idx);
 }
+// candidate-list entries as the search epilogue stores them: (index << 32) | raw fp32 score bits
+__device__ __forceinline__ unsigned long long raw_to_key(unsigned long long raw) {
+    return make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
+}
 __device__ __forceinline__ float key_score(unsigned long long k) {
     return ordered_to_float((uint32_t)(k >> 32));
 }
 __device__ __forceinline__ uint32_t key_index(unsigned long long k) {
     return 0xffffffffu - (uint32_t)(k & 0xffffffffull);
+}
+
+__device__ __forceinline__ unsigned long long key_to_raw(unsigned long long k) {
+    return ((unsigned long long)key_index(k) << 32) | (unsigned long long)__float_as_uint(key_score(k));
 }
 
 #endif  // __CUDACC__

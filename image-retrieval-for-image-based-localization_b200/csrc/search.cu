@@ -27,6 +27,7 @@
 #include "search.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace cir {
 
@@ -58,7 +59,7 @@ struct SearchParams {
     const int32_t* db_label;     // optional [N]: candidates with db_label == q_label are skipped
     float* dense_out;            // MODE_DENSE: [Q, dense_ld]
     long long dense_ld;
-    int b_evict_first;
+    int b_policy;                // database tiles: 0 evict_last, 1 evict_first, 2 evict_normal
 };
 
 // ---------------------------------------------------------------------------------------
@@ -71,7 +72,7 @@ __device__ __noinline__ void compact_row(unsigned long long* L, int n, int k, in
 #pragma unroll
     for (int r = 0; r < KPL; ++r) {
         const int e = r * 32 + lane;
-        key[r] = e < n ? __ldcg(L + e) : 0ull;
+        key[r] = e < n ? raw_to_key(__ldcg(L + e)) : 0ull;
     }
     // largest T with |{hi >= T}| >= k  ==  the k-th largest ordered score
     uint32_t T = 0;
@@ -107,7 +108,7 @@ __device__ __noinline__ void compact_row(unsigned long long* L, int n, int k, in
     for (int r = 0; r < KPL; ++r) {
         const bool keep = key[r] >= T64 && key[r] != 0ull;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) L[base + __popc(bal & lt)] = key[r];
+        if (keep) L[base + __popc(bal & lt)] = key_to_raw(key[r]);
         base += __popc(bal);
     }
     __syncwarp();
@@ -174,7 +175,7 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // query tiles the database tiles are shared through L2 by the CTAs of the same split (evict_last
             // measured 15 % faster than evict_normal on 10k x 1M); with one query tile they are read once.
             const uint64_t pol_a = policy_evict_last();
-            const uint64_t pol_b = P.b_evict_first ? policy_evict_first() : policy_evict_last();
+            const uint64_t pol_b = P.b_policy == 1 ? policy_evict_first() : (P.b_policy == 2 ? policy_evict_normal() : policy_evict_last());
             int stage = 0;
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
@@ -258,15 +259,41 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const int cb = col0 + c * 32;
                     if (MODE == MODE_TOPK) {
                         if (valid) {
+                            if (P.db_label || cb + 32 > P.N) {
+                                // mining (label exclusion) and the ragged last tile: checked path
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float sc = __uint_as_float(v[j]);
-                                if (sc > tau) {
-                                    const int idx = cb + j;
-                                    bool ok = idx < P.N;
-                                    if (ok && P.db_label) ok = __ldg(P.db_label + idx) != qlab;
-                                    if (ok) L[cnt++] = make_key(sc, (uint32_t)idx);
+                                for (int j = 0; j < 32; ++j) {
+                                    const float sc = __uint_as_float(v[j]);
+                                    if (sc > tau) {
+                                        const int idx = cb + j;
+                                        bool ok = idx < P.N;
+                                        if (ok && P.db_label) ok = __ldg(P.db_label + idx) != qlab;
+                                        if (ok) L[cnt++] = ((unsigned long long)(uint32_t)idx << 32) | (unsigned long long)v[j];
+                                    }
                                 }
+                            } else {
+                                // Branch-free: one epilogue warp runs alone on its scheduler, so every taken branch costs
+                                // its full latency (measured: ~165 cycles per append, which put the epilogue on the MMA's
+                                // critical path).  Predicated store + predicated bump of a 32-bit byte offset instead.
+                                uint32_t off = (uint32_t)cnt * 8u;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const uint32_t ix = (uint32_t)(cb + j);
+                                    asm volatile(
+                                        "{\n\t"
+                                        ".reg .pred p;\n\t"
+                                        ".reg .u64 a;\n\t"
+                                        "setp.gt.f32 p, %2, %3;\n\t"
+                                        "@p cvt.u64.u32 a, %0;\n\t"
+                                        "@p add.u64 a, a, %1;\n\t"
+                                        "@p st.global.v2.b32 [a], {%4, %5};\n\t"
+                                        "@p add.u32 %0, %0, 8;\n\t"
+                                        "}"
+                                        : "+r"(off)
+                                        : "l"(L), "f"(__uint_as_float(v[j])), "f"(tau), "r"(v[j]), "r"(ix)
+                                        : "memory");
+                                }
+                                cnt = (int)(off >> 3);
                             }
                         }
                         const unsigned need = __ballot_sync(0xffffffffu, valid && (cnt + 32 > P.cap));
@@ -349,9 +376,12 @@ static int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
     return CIR_OK;
 }
 
+// candidate list capacity: room for ~3k appends beyond the k kept, so that after the threshold warm start a
+// list almost never has to be compacted inside the GEMM kernel (compaction stalls the MMA pipeline)
 int search_cap_for_k(int k) {
+    if (const char* e = getenv("CIR_DEBUG_CAP")) return atoi(e);   // tuning aid
     int cap = 128;
-    while (cap < k + 96) cap <<= 1;
+    while (cap < k + 96 || (cap < 4 * k && cap < 1024)) cap <<= 1;
     return cap;
 }
 
@@ -394,7 +424,8 @@ static int launch_search(int mode, const void* q, int Q, const void* db, long lo
     P.N = (int)N;
     P.kblocks = Kd / BK;
     P.mt = plan.mt; P.nt = plan.nt; P.S = plan.S; P.tps = plan.tps; P.units = plan.units; P.Qpad = plan.Qpad;
-    P.b_evict_first = plan.mt == 1;
+    P.b_policy = plan.mt == 1 ? 1 : 0;
+    if (const char* e = getenv("CIR_DEBUG_BPOL")) P.b_policy = atoi(e);   // tuning aid
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

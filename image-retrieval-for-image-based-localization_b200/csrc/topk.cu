@@ -60,12 +60,96 @@ struct SelParams {
 };
 
 constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SEL_MAX_KOUT = 1024;    // largest k the select / merge kernel emits
+constexpr int SEL_SMEM_BYTES = SEL_N * 8 + SEL_MAX_KOUT * 8 + SEL_WARPS * 256 * 4 + (2 * SEL_MAX_LISTS + 1 + 4 + 3) * 4;
+
+template <int SRC> __global__ void topk_select_kernel(const struct SelParams p);
+template <int SRC>
+static int launch_select(const struct SelParams& p, int Q, cudaStream_t stream);
+
+// Keep the k largest of buf[0, fill) (fill > k): MSB-first radix select of the k-th largest 64-bit key
+// (8 passes of 8 bits, per-warp histograms), then the survivors are moved to buf[0, k) (unordered).
+// Far cheaper than sorting: ~8 x (fill / 512) key reads per thread instead of ~78 x 4 compare-exchanges.
+__device__ __forceinline__ void block_keep_topk(unsigned long long* buf, int fill, int k, int* hist /*[SEL_WARPS][256]*/,
+                                                unsigned long long* stage /*[SEL_MAX_KOUT]*/, int* s_misc /*[4]*/, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned long long prefix = 0ull;
+    int krem = k;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int t = tid; t < SEL_WARPS * 256; t += SEL_THREADS) hist[t] = 0;
+        __syncthreads();
+        for (int t = tid; t < fill; t += SEL_THREADS) {
+            const unsigned long long key = buf[t];
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                atomicAdd(&hist[warp * 256 + (int)((key >> shift) & 255ull)], 1);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < SEL_WARPS; ++w) c += hist[w * 256 + tid];
+            hist[tid] = c;                     // row 0 = block histogram
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins 255 - 8 l ... 248 - 8 l (descending); find the bin where the running count reaches krem
+            int c[8], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = hist[255 - 8 * lane - i]; tot += c[i]; }
+            int inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int before = inc - tot;                     // keys in higher bins than this lane's
+            const bool mine = before < krem && krem <= inc;
+            if (mine) {
+                int run = before, bin = 255 - 8 * lane;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (run + c[i] >= krem) { bin = 255 - 8 * lane - i; break; }
+                    run += c[i];
+                }
+                s_misc[0] = bin;
+                s_misc[1] = krem - run;
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)s_misc[0] << shift;
+        krem = s_misc[1];
+    }
+    // prefix == the k-th largest key.  Survivors: everything greater, then equals until k are kept.
+    if (tid == 0) { s_misc[2] = 0; }
+    __syncthreads();
+    for (int t = tid; t < fill; t += SEL_THREADS) {
+        const unsigned long long key = buf[t];
+        if (key > prefix) stage[atomicAdd(&s_misc[2], 1)] = key;
+    }
+    __syncthreads();
+    for (int t = tid; t < fill; t += SEL_THREADS) {
+        const unsigned long long key = buf[t];
+        if (key == prefix) {
+            const int pos = atomicAdd(&s_misc[2], 1);
+            if (pos < k) stage[pos] = key;
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < k; t += SEL_THREADS) buf[t] = stage[t];
+    __syncthreads();
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParams p) {
-    __shared__ unsigned long long buf[SEL_N];
-    __shared__ int s_cnt[SEL_MAX_LISTS];      // list sizes of the current window of lists
-    __shared__ int s_off[SEL_MAX_LISTS + 1];  // exclusive prefix sums
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(sel_smem);          // [SEL_N]
+    unsigned long long* stage = buf + SEL_N;                                            // [SEL_MAX_KOUT]
+    int* hist = reinterpret_cast<int*>(stage + SEL_MAX_KOUT);                            // [SEL_WARPS][256]
+    int* s_cnt = hist + SEL_WARPS * 256;      // [SEL_MAX_LISTS] list sizes of the current window of lists
+    int* s_off = s_cnt + SEL_MAX_LISTS;       // [SEL_MAX_LISTS + 1] exclusive prefix sums
+    int* s_misc = s_off + SEL_MAX_LISTS + 1;  // [4]
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int fill = 0;
@@ -99,12 +183,12 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
             int take = done;
             while (take < win && s_off[take + 1] - start <= room) ++take;    // uniform across threads
             // warp w copies lists done + w, done + w + 16, ...
-            for (int g = done + warp; g < take; g += SEL_THREADS / 32) {
+            for (int g = done + warp; g < take; g += SEL_WARPS) {
                 const int c = s_cnt[g];
                 const int dst = fill + s_off[g] - start;
                 if (SRC == 0) {
                     const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
-                    for (int t = lane; t < c; t += 32) buf[dst + t] = __ldcg(L + t);
+                    for (int t = lane; t < c; t += 32) buf[dst + t] = raw_to_key(__ldcg(L + t));
                 } else {
                     const size_t o = ((size_t)(g0 + g) * p.Q + q) * p.kin;
                     for (int t = lane; t < c; t += 32) {
@@ -115,19 +199,20 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
             }
             fill += s_off[take] - start;
             done = take;
-            const int P = next_pow2(fill);
-            for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
             __syncthreads();
-            block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
-            if (fill > p.k) fill = p.k;
+            if (fill > p.k) {
+                block_keep_topk(buf, fill, p.k, hist, stage, s_misc, tid);
+                fill = p.k;
+            }
         }
         g0 += win;
         __syncthreads();
     }
-    if (p.G == 0) {
-        for (int t = tid; t < p.k; t += SEL_THREADS) buf[t] = 0ull;
-        __syncthreads();
-    }
+    // final ordering of the <= k survivors
+    const int P = next_pow2(fill);
+    for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
+    __syncthreads();
+    block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
     for (int t = tid; t < p.k; t += SEL_THREADS) {
         const unsigned long long key = t < fill ? buf[t] : 0ull;
         const bool ok = key != 0ull;
@@ -209,6 +294,20 @@ int launch_row_kth_largest(const float* scores, int Q, int n, long long ld, int 
     return CIR_OK;
 }
 
+template <int SRC>
+static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
+    static thread_local int attr_dev = -1;
+    const DeviceInfo& dev = device_info();
+    if (attr_dev != dev.device) {
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
+        attr_dev = dev.device;
+    }
+    topk_select_kernel<SRC><<<Q, SEL_THREADS, SEL_SMEM_BYTES, stream>>>(p);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
+}
+
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
                              float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream) {
     CIR_REQUIRE(k + cap <= SEL_N, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_N);
@@ -216,10 +315,7 @@ int launch_topk_select_lists(const unsigned long long* lists, const int* counts,
     p.lists = lists; p.counts = counts; p.Qpad = Qpad; p.cap = cap;
     p.G = S; p.Q = Q; p.k = k;
     p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = out_ld; p.idx_offset = idx_offset;
-    topk_select_kernel<0><<<Q, SEL_THREADS, 0, stream>>>(p);
-    CIR_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-    return CIR_OK;
+    return launch_select<0>(p, Q, stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -331,16 +427,14 @@ extern "C" int cir_topk_merge(const float* scores, const int32_t* idx, int G, in
                               int32_t* out_idx, int k_out, void* stream) {
     CIR_REQUIRE(scores && idx && out_scores && out_idx, CIR_ERR_INVALID_ARG, "cir_topk_merge: null pointer");
     CIR_REQUIRE(G >= 1 && Q >= 0 && k >= 1 && k_out >= 1, CIR_ERR_INVALID_ARG, "cir_topk_merge: bad shape");
-    CIR_REQUIRE(k_out + k <= SEL_N, CIR_ERR_UNSUPPORTED, "cir_topk_merge: k_out + k = %d exceeds %d", k_out + k, SEL_N);
+    CIR_REQUIRE(k_out + k <= SEL_N && k_out <= SEL_MAX_KOUT, CIR_ERR_UNSUPPORTED,
+                "cir_topk_merge: k_out + k = %d exceeds %d (or k_out > %d)", k_out + k, SEL_N, SEL_MAX_KOUT);
     if (Q == 0) return CIR_OK;
     SelParams p{};
     p.in_scores = scores; p.in_idx = idx; p.kin = k;
     p.G = G; p.Q = Q; p.k = k_out;
     p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = k_out; p.idx_offset = 0;
-    topk_select_kernel<1><<<Q, SEL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
-    CIR_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-    return CIR_OK;
+    return launch_select<1>(p, Q, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cir_rescore_topk(const float* q32, int Q, const float* db32, int64_t N, int D, const int32_t* cand,

@@ -31,8 +31,12 @@ elif what in ("search10k", "search70"):
         S.pack_rows(blk / blk.norm(dim=1, keepdim=True), "db", "bf16", out=dbp[a:a + 125_000])
     q = torch.randn((Q, D), device=dev)
     qp = S.pack_rows(q / q.norm(dim=1, keepdim=True), "query", "bf16")
+    tau = None
+    if len(sys.argv) > 3 and sys.argv[3] == "tau":
+        s0, _ = S.search_packed(qp, dbp, 100)
+        tau = (s0[:, -1] - 1e-4).contiguous()
     for i in range(n):
-        S.search_packed(qp, dbp, 100)
+        S.search_packed(qp, dbp, 100, tau0=tau)
 elif what == "mining":
     from cirtorch_b200.mining import mine_hard_negatives_rows
     q = torch.randn((2000, 2048), device=dev)
