@@ -30,6 +30,7 @@ import torch
 
 B, C, H, W, DOUT = 64, 2048, 32, 32, 2048
 TAIL_BYTES = B * C * H * W * 4 + DOUT * C * 4 + DOUT * 4 + B * DOUT * 4          # 554,180,608
+TAIL_NCU_TRAFFIC = 553_767_680 + 7_017_728      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/)
 DB_N, DB_D, TOPK = 1_000_000, 2048, 100
 METRIC = "descriptors/s (GeM+whiten tail) & queries/s vs 1M×2048 DB at 1/2/4/8 B200, %roofline"
 
@@ -43,59 +44,98 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+_SAMPLER_CODE = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+out = open(sys.argv[2], "w", buffering=1)
+out.write("max %d\n" % nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+while True:
+    try:
+        mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        out.write("%.6f %d %d\n" % (time.time(), mhz, r))
+    except Exception:
+        pass
+    time.sleep(0.0005)
+"""
+
+
 class ClockSampler:
-    """NVML clocks / throttle reasons sampled in a thread while the timed region runs."""
+    """SM clock / throttle reasons sampled by NVML in a SEPARATE process (no GIL contention with the launch
+    loop) while the timed region runs; samples are matched to the region by wall-clock time stamps."""
 
     def __init__(self, index):
-        self.samples = []
-        self.stop = False
-        self.mark = 0
-        self.ok = False
+        import subprocess
+        import tempfile
+        self.path = tempfile.mktemp(prefix="cir_clocks_")
+        self.t0 = self.t1 = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception as e:  # noqa: BLE001
-            self.err = str(e)
-        self.t = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        nv = self.nv
-        while not self.stop:
-            try:
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            phys = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
                 try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:  # noqa: BLE001
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((self.mark, mhz, r))
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.002)
+                    phys = int(vis.split(",")[index])
+                except ValueError:
+                    phys = index
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CODE, str(phys), self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
 
     def start(self):
-        if self.ok:
-            self.t.start()
+        # give the child time to initialise NVML
+        t_end = time.time() + 5.0
+        while self.proc and time.time() < t_end and not (os.path.exists(self.path) and os.path.getsize(self.path) > 20):
+            time.sleep(0.01)
+
+    @property
+    def mark(self):
+        return 0
+
+    @mark.setter
+    def mark(self, v):
+        if v == 1:
+            self.t0 = time.time()
+        elif v == 2:
+            self.t1 = time.time()
 
     def finish(self):
-        self.stop = True
-        if not self.ok:
+        if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
-        self.t.join(1.0)
-        timed = [s for s in self.samples if s[0] == 1] or self.samples[-5:]
-        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
-                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
-                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        time.sleep(0.005)
+        self.proc.kill()
+        self.proc.wait()
+        max_mhz, samples = None, []
+        try:
+            for line in open(self.path):
+                f = line.split()
+                if f and f[0] == "max":
+                    max_mhz = int(f[1])
+                elif len(f) == 3:
+                    samples.append((float(f[0]), int(f[1]), int(f[2])))
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if not samples:
+            return {"sm_mhz": None, "sm_max_mhz": max_mhz, "reasons": ["nvml unavailable"]}
+        timed = [s for s in samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        inside = len(timed)
+        if not timed:   # region shorter than the sampling period: take the samples closest to it
+            timed = sorted(samples, key=lambda s: abs(s[0] - (self.t0 or s[0])))[:3]
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                 0x100: "display_clock_setting"}
         bits = 0
         for s in timed:
             bits |= s[2]
-        reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
         mhz = sorted(s[1] for s in timed)
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(timed)}
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": max_mhz, "reasons": [n for b, n in names.items() if bits & b],
+                "samples": inside}
 
 
 def dist_env():
@@ -145,6 +185,7 @@ def make_head(dev):
 def cpu_tail_baseline(budget_s=12.0, max_iters=30):
     """The oracle port of globalHead.forward on the host cores, batch 64 x 2048 x 32 x 32."""
     from oracle import cirtorch_oracle as O
+    host_threads()
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, H, W))
     Wt = torch.empty(DOUT, C)
@@ -178,10 +219,21 @@ def cpu_search_baseline(n_rows=100_000, q=70, budget_s=10.0):
             "sample": "np.dot + np.argsort, %d queries x %d rows x %d, time scaled linearly to 1M rows" % (q, n_rows, DB_D)}
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    host_threads()
     from oracle import cirtorch_oracle as O
     torch.manual_seed(0)
     x = torch.relu(torch.randn(B, C, H, W))
@@ -372,8 +424,9 @@ def main():
                                           "(configs[3]); strong scaling"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None,
-                         "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth" % pk["src"]},
+                         "frac": achieved / pk["hbm_gbs"], "traffic": TAIL_NCU_TRAFFIC,
+                         "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth; "
+                                 "traffic = dram read+write per launch from profiles/r1_tail_tma_mma.txt" % pk["src"]},
             "search": search,
         }
         if not args.no_cpu_baseline and world == 1:

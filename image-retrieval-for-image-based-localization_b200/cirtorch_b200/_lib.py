@@ -42,6 +42,7 @@ SIGNATURES = {
     "cir_rescore_topk": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _c_int, C.c_int32, _vp, _vp, _c_int, _vp]),
     "cir_qe_aggregate": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_f, _c_i64,
                                   _c_f, _vp, _vp]),
+    "cir_eval_ap": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
     "cir_mine_filter": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
 }
 

@@ -25,16 +25,20 @@ def world(group=None):
 
 
 def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None):
-    """all_gather of per-shard lists [Q, k] -> ([G, Q, k] scores, [G, Q, k] idx), shard order = rank order."""
+    """all_gather of per-shard lists [Q, k] -> ([G, Q, k] scores, [G, Q, k] idx), shard order = rank order.
+
+    Scores (fp32) and indices (int32) travel in ONE collective as a [Q, 2k] 32-bit buffer."""
     _, ws = world(group)
     if ws == 1:
         return scores[None], idx[None]
-    Q = scores.shape[0]
-    s_all = torch.empty((ws * Q,) + tuple(scores.shape[1:]), dtype=scores.dtype, device=scores.device)
-    i_all = torch.empty((ws * Q,) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(s_all, scores.contiguous(), group=group)     # concatenation along dim 0
-    dist.all_gather_into_tensor(i_all, idx.contiguous(), group=group)
-    return s_all.view((ws,) + tuple(scores.shape)), i_all.view((ws,) + tuple(idx.shape))
+    Q, k = scores.shape
+    both = torch.empty((Q, 2 * k), dtype=torch.int32, device=scores.device)
+    both[:, :k] = scores.contiguous().view(torch.int32)
+    both[:, k:] = idx.to(torch.int32)
+    out = torch.empty((ws * Q, 2 * k), dtype=torch.int32, device=scores.device)
+    dist.all_gather_into_tensor(out, both, group=group)                       # concatenation along dim 0
+    out = out.view(ws, Q, 2 * k)
+    return out[:, :, :k].contiguous().view(torch.float32), out[:, :, k:].contiguous()
 
 
 class ShardedIndex:

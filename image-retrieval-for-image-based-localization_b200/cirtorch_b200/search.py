@@ -55,6 +55,8 @@ def pack_rows(x_rows: torch.Tensor, role: str, mode: str = "bf16", out: torch.Te
     Kd = packed_width(D, mode)
     if out is None:
         out = torch.empty((rows, Kd), dtype=torch.bfloat16, device=x_rows.device)
+    if rows == 0:
+        return out
     rc = lib.cir_pack_bf16(_lib.ptr(x_rows), rows, D, D, _lib.ptr(out), Kd, _SPLIT[mode],
                            0 if role == "query" else 1, _lib.stream_of(x_rows))
     _lib.check(rc, "cir_pack_bf16")
@@ -124,7 +126,7 @@ def search_topk_rows(q_rows, db_rows, k, mode="bf16", rescore=None, db_packed=No
         rescore = mode == "bf16" and db_rows is not None
     qp = pack_rows(q_rows, "query", mode)
     dbp = db_packed if db_packed is not None else pack_rows(db_rows, "db", mode)
-    if not rescore:
+    if not rescore or q_rows.shape[0] == 0 or dbp.shape[0] == 0:
         return search_packed(qp, dbp, k, idx_offset, q_label=q_label, db_label=db_label)
     kc = min(rescore_pad(k), max(k, dbp.shape[0]))
     kc = min(kc, MAX_K)
@@ -193,6 +195,8 @@ def merge_topk(scores, idx, k_out=None):
     idx = idx.to(torch.int32).contiguous()
     out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((Q, k_out), dtype=torch.int32, device=scores.device)
+    if Q == 0:
+        return out_s, out_i
     rc = lib.cir_topk_merge(_lib.ptr(scores), _lib.ptr(idx), G, Q, k, _lib.ptr(out_s), _lib.ptr(out_i), k_out,
                             _lib.stream_of(scores))
     _lib.check(rc, "cir_topk_merge")

@@ -344,7 +344,20 @@ rescore_kernel(const float* __restrict__ q32, const float* __restrict__ db32, lo
             const float* v = db32 + (size_t)row * D;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             if (vec) {
-                for (int d = lane * 4; d < D; d += 128) {
+                // 8 x 512 B of the row in flight per warp (the gather is latency-bound otherwise)
+                int d = lane * 4;
+                for (; d + 7 * 128 < D; d += 8 * 128) {
+                    float4 x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = ld_stream_f4(reinterpret_cast<const float4*>(v + d + u * 128));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 y = *reinterpret_cast<const float4*>(qv + d + u * 128);
+                        a0 = fmaf(x[u].x, y.x, a0); a1 = fmaf(x[u].y, y.y, a1);
+                        a2 = fmaf(x[u].z, y.z, a2); a3 = fmaf(x[u].w, y.w, a3);
+                    }
+                }
+                for (; d < D; d += 128) {
                     const float4 x = __ldg(reinterpret_cast<const float4*>(v + d));
                     const float4 y = *reinterpret_cast<const float4*>(qv + d);
                     a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);

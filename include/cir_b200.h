@@ -180,6 +180,20 @@ int cir_mine_filter(const int32_t* cand, int Q, int Kc,
                     int nnum, const float* q32, const float* pool32, int D,
                     int32_t* out_sel, int32_t* out_count, float* out_dist, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * 6. Evaluation of ranked lists (the consumer of the ranking step)
+ *    replaces compute_ap / compute_map    cirtorch/utils/evaluation/ParisOxfordEval.py:4-113
+ *    ranks [Q, ld] int32 row-major (row q = database indices best first, R entries used;
+ *    negative entries = padding), positives / junk per query as CSR lists of SORTED indices
+ *    (ok_off [Q+1], ok_idx; junk_off [Q+1], junk_idx).  Junk entries ranked before a positive
+ *    move it up (:86-96); ap_out [Q] fp64 (NaN for a query without positives, :69-73);
+ *    prs_out [Q, nk] = precision at kappas[j] with kq = min(max rank of a positive, kappa).
+ * ------------------------------------------------------------------------------------ */
+int cir_eval_ap(const int32_t* ranks, int Q, int64_t R, int64_t ld,
+                const int32_t* ok_off, const int32_t* ok_idx,
+                const int32_t* junk_off, const int32_t* junk_idx,
+                const int32_t* kappas, int nk, double* ap_out, double* prs_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

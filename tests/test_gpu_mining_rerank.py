@@ -163,3 +163,39 @@ def test_extract_vectors_resnet50_end_to_end():
     scores, ranks = S.rank(vecs.to(DEV), vecs[:, :3].to(DEV))
     s_ref, r_ref = O.rank(ref.numpy(), ref[:, :3].numpy())
     assert (ranks[0].cpu().numpy() == np.arange(3)).all()
+
+
+def test_compute_map_golden_and_end_to_end(golden):
+    """N1: device mAP vs the reference fixture, then ranks from the search kernel -> identical mAP to the oracle."""
+    from cirtorch_b200 import evaluate as E, search as S
+    g = golden("eval")
+    nq = int(g["nq"])
+    gnd = [{"ok": g[f"ok{i}"], "junk": g[f"junk{i}"]} for i in range(nq)]
+    mp, aps, pr, prs = E.compute_map(g["ranks"], gnd, [1, 5, 10])
+    np.testing.assert_allclose(mp, g["map"], rtol=1e-12)
+    np.testing.assert_allclose(aps, g["aps"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(pr, g["pr"], rtol=1e-12)
+    np.testing.assert_allclose(prs, g["prs"], rtol=1e-12, equal_nan=True)
+    assert abs(E.compute_ap(np.array([0, 3, 4, 10]), 6) - float(g["ap_direct"])) < 1e-12
+    # end to end on synthetic descriptors (rOxford shape, revisited protocol)
+    db, lab = clustered_unit_rows(4993, 256, 60, 0.7, seed=21)
+    q, qlab = clustered_unit_rows(70, 256, 60, 0.7, seed=21)
+    rs = np.random.RandomState(3)
+    gnd2 = []
+    for i in range(70):
+        same = np.flatnonzero(lab == qlab[i])
+        rs.shuffle(same)
+        a, b = len(same) // 3, 2 * len(same) // 3
+        gnd2.append({"easy": same[:a], "hard": same[a:b], "junk": same[b:]})
+    if len(gnd2[0]["easy"]) == 0:
+        gnd2[0]["easy"] = gnd2[0]["hard"][:1]
+    scores, ranks = S.rank(_dev(db.T.copy()), _dev(q.T.copy()))
+    ref_scores, ref_ranks = O.rank(db.T, q.T)
+    logs = []
+    out = E.compute_map_and_print("roxford5k", ranks, gnd2, lambda fmt, *a: logs.append(fmt % a))
+    ref = O.compute_map_revisited(ref_ranks, gnd2, (1, 5, 10))
+    assert abs(out["mAP"] - ref["mAP"]) < 1e-6 and len(logs) == 4
+    # top-k lists are accepted too: with k >= the last positive's rank the AP is unchanged
+    mp_full, _, _, _ = E.compute_map(ranks, [{"ok": np.concatenate([g2["easy"], g2["hard"]]), "junk": g2["junk"]} for g2 in gnd2])
+    mp_top, _, _, _ = E.compute_map(ranks[:4000], [{"ok": np.concatenate([g2["easy"], g2["hard"]]), "junk": g2["junk"]} for g2 in gnd2])
+    assert mp_top <= mp_full + 1e-12

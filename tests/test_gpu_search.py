@@ -51,6 +51,7 @@ def test_pack_bf16_roundtrip():
     (129, 1000, 128, 5),       # two query tiles, one ragged
     (33, 257, 192, 257 if 257 <= 512 else 512),   # k == N
     (16, 50, 64, 64),          # k > N: -1 / -inf padding
+    (40, 3000, 100, 512),      # D not a multiple of 64 (zero-padded operands), largest fused k
 ])
 def test_topk_matches_oracle(Q, N, D, k):
     from cirtorch_b200 import search as S
@@ -162,6 +163,30 @@ def test_equal_scores_flood():
     q = np.random.RandomState(7).randn(3, 64).astype(np.float32)
     s, i = S.search_topk_rows(_dev(q), _dev(db), 100, mode="bf16")
     np.testing.assert_array_equal(i.cpu().numpy(), np.tile(np.arange(100, dtype=np.int32), (3, 1)))
+
+
+def test_empty_inputs():
+    from cirtorch_b200 import search as S
+    db = torch.randn(100, 64, device=DEV)
+    s, i = S.search_topk_rows(torch.zeros(0, 64, device=DEV), db, 5)
+    assert s.shape == (0, 5) and i.shape == (0, 5)
+    s, i = S.search_packed(S.pack_rows(db[:3].contiguous(), "query"), torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16), 4)
+    assert bool((i == -1).all()) and bool(torch.isinf(s).all())
+    assert S.merge_topk(torch.zeros(2, 0, 4, device=DEV), torch.zeros(2, 0, 4, device=DEV, dtype=torch.int32)).__len__() == 2
+
+
+def test_ties_across_splits():
+    """Equal scores in different database tiles / splits: the lower index must win everywhere."""
+    from cirtorch_b200 import search as S
+    rs = np.random.RandomState(11)
+    base = rs.randn(50, 64).astype(np.float32)
+    db = np.tile(base, (2000, 1))                        # 100,000 rows, every row repeated 2000 times
+    q = base[:7] + 0.01 * rs.randn(7, 64).astype(np.float32)
+    s, i = S.search_topk_rows(_dev(q), _dev(db), 300, mode="bf16", rescore=False)
+    i = i.cpu().numpy()
+    for r in range(7):
+        # best match = base row r: its 2000 copies sit at r, r + 50, r + 100, ... -> the first 300 of them, ascending
+        np.testing.assert_array_equal(i[r], r + 50 * np.arange(300))
 
 
 def test_bad_arguments_raise():

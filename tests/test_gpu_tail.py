@@ -52,6 +52,9 @@ def test_golden_fixtures(golden):
     ((7, 512, 19, 23), 3.0),       # HW % 4 != 0: scalar path
     ((130, 96, 4, 4), 2.0),        # more images than one phase-B pass (64)
     ((1, 64, 1, 1), 3.0),
+    ((2, 64, 80, 80), 3.0),        # rows of 25.6 KB: larger than a TMA ring slot -> direct-load path
+    ((3, 4096, 8, 8), 3.0),        # C > 2048: two K tiles of the projection weights
+    ((70, 32, 2, 2), 4.0),         # tiny rows, many per ring slot
 ])
 def test_head_vs_oracle(shape, p):
     torch.manual_seed(0)
