@@ -55,10 +55,11 @@ if what in ("all", "tail", "stamps"):
                               _lib.ptr(out), 2048, _lib.ptr(ws), ws.numel(), 0x80000000, None)
         assert rc == 0
         torch.cuda.synchronize()
-    st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :6].cpu().double()
+    st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :8].cpu().double()
+    st = st[st[:, 3] > st[:, 2]]      # CTAs that own an output chunk
     t0 = st[:, 0].min()
-    names = ["start", "endA", "sync1", "endB", "sync2", "end"]
-    for j in range(6):
+    names = ["start", "endA", "sync1", "endB", "sync2", "end", "B:Wready", "B:kloop"]
+    for j in range(8):
         col = (st[:, j] - t0) / 1e3
         print(f"stamp {names[j]:6s}: min {col.min():8.1f} us  mean {col.mean():8.1f}  max {col.max():8.1f}")
 if what in ("all", "search"):
