@@ -283,13 +283,15 @@ def bench_search(dev, rank, world, pk, steps, warmup):
         q32 = q32 / q32.norm(dim=1, keepdim=True)
         qp = S.pack_rows(q32, "query", "bf16")
 
+        both, views = P.topk_exchange_buffer(Q, TOPK, dev)
+
         def step_local():
-            return S.search_packed(qp, dbp, TOPK, idx_offset=lo)
+            return S.search_packed(qp, dbp, TOPK, idx_offset=lo, out=views)
 
         def step():
             s, i = step_local()
             if world > 1:
-                s_all, i_all = P.gather_topk(s, i)
+                s_all, i_all = P.gather_topk(s, i, both=both)
                 s, i = S.merge_topk(s_all, i_all, TOPK)
             return s, i
 

@@ -38,7 +38,7 @@ SIGNATURES = {
     "cir_scores_dense": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _c_i64, _vp]),
     "cir_sort_rows_workspace_bytes": (_c_int, [_c_int, _c_i64, _szp]),
     "cir_sort_rows_desc": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, C.c_size_t, _vp]),
-    "cir_topk_merge": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp]),
+    "cir_topk_merge": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_i64, _vp, _vp, _c_int, _vp]),
     "cir_rescore_topk": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _c_int, C.c_int32, _vp, _vp, _c_int, _vp]),
     "cir_qe_aggregate": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_f, _c_i64,
                                   _c_f, _vp, _vp]),

@@ -24,21 +24,30 @@ def world(group=None):
     return 0, 1
 
 
-def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None):
+def topk_exchange_buffer(Q: int, k: int, device):
+    """One 32-bit buffer [2, Q, k] whose halves are the local (scores fp32, idx int32) lists: the search writes
+    into it directly and it travels in ONE collective."""
+    both = torch.empty((2, Q, k), dtype=torch.int32, device=device)
+    return both, (both[0].view(torch.float32), both[1])
+
+
+def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None, both: torch.Tensor = None):
     """all_gather of per-shard lists [Q, k] -> ([G, Q, k] scores, [G, Q, k] idx), shard order = rank order.
 
-    Scores (fp32) and indices (int32) travel in ONE collective as a [Q, 2k] 32-bit buffer."""
+    Scores (fp32) and indices (int32) travel in ONE collective as a [2, Q, k] 32-bit buffer (pass ``both`` from
+    :func:`topk_exchange_buffer` to skip the packing copy); the results are strided views of the gathered buffer."""
     _, ws = world(group)
     if ws == 1:
         return scores[None], idx[None]
     Q, k = scores.shape
-    both = torch.empty((Q, 2 * k), dtype=torch.int32, device=scores.device)
-    both[:, :k] = scores.contiguous().view(torch.int32)
-    both[:, k:] = idx.to(torch.int32)
-    out = torch.empty((ws * Q, 2 * k), dtype=torch.int32, device=scores.device)
+    if both is None:
+        both = torch.empty((2, Q, k), dtype=torch.int32, device=scores.device)
+        both[0] = scores.contiguous().view(torch.int32)
+        both[1] = idx.to(torch.int32)
+    out = torch.empty((ws * 2, Q, k), dtype=torch.int32, device=scores.device)
     dist.all_gather_into_tensor(out, both, group=group)                       # concatenation along dim 0
-    out = out.view(ws, Q, 2 * k)
-    return out[:, :, :k].contiguous().view(torch.float32), out[:, :, k:].contiguous()
+    out = out.view(ws, 2, Q, k)
+    return out[:, 0].view(torch.float32), out[:, 1]
 
 
 class ShardedIndex:
@@ -64,7 +73,7 @@ class ShardedIndex:
         if self.world_size == 1:
             return s, i
         s_all, i_all = gather_topk(s, i, self.group)
-        return merge_topk(s_all, i_all, k)
+        return merge_topk(s_all, i_all, k)      # strided views of the gathered buffer, merged in place
 
 
 def extract_vectors_dp(net, images, group=None, **kw):

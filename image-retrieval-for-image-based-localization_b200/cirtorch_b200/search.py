@@ -64,7 +64,7 @@ def pack_rows(x_rows: torch.Tensor, role: str, mode: str = "bf16", out: torch.Te
 
 
 def search_packed(qp: torch.Tensor, dbp: torch.Tensor, k: int, idx_offset: int = 0, tau0=None,
-                  q_label=None, db_label=None):
+                  q_label=None, db_label=None, out=None):
     """Top-k of packed operands: (scores [Q, k] fp32, idx [Q, k] int32), sorted (score desc, idx asc)."""
     _lib.require_cuda(qp, dbp, tau0, q_label, db_label)
     lib = _lib.load()
@@ -74,8 +74,11 @@ def search_packed(qp: torch.Tensor, dbp: torch.Tensor, k: int, idx_offset: int =
         raise ValueError("query / database operand widths differ: %d vs %d" % (Kd, dbp.shape[1]))
     if not 1 <= k <= MAX_K:
         raise ValueError("k=%d outside [1, %d]; use rank() for full rankings" % (k, MAX_K))
-    scores = torch.empty((Q, k), dtype=torch.float32, device=qp.device)
-    idx = torch.empty((Q, k), dtype=torch.int32, device=qp.device)
+    if out is not None:        # caller-provided contiguous [Q, k] buffers (fp32 scores, int32 indices)
+        scores, idx = out
+    else:
+        scores = torch.empty((Q, k), dtype=torch.float32, device=qp.device)
+        idx = torch.empty((Q, k), dtype=torch.int32, device=qp.device)
     if Q == 0:
         return scores, idx
     if N == 0:
@@ -186,18 +189,28 @@ def rank(database_vecs, qvecs, mode="bf16x3"):
 
 
 def merge_topk(scores, idx, k_out=None):
-    """Merge G sorted top-k lists per query: [G, Q, k] -> [Q, k_out] (cir_topk_merge)."""
+    """Merge G sorted top-k lists per query: [G, Q, k] -> [Q, k_out] (cir_topk_merge).
+
+    ``scores`` / ``idx`` may be strided views along G (e.g. the two halves of one all-gathered buffer)."""
     _lib.require_cuda(scores, idx)
     lib = _lib.load()
     G, Q, k = scores.shape
     k_out = k if k_out is None else k_out
-    scores = scores.float().contiguous()
-    idx = idx.to(torch.int32).contiguous()
+    def dense_lists(t, dtype):
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        ok = t.stride(2) == 1 and t.stride(1) == k and (G == 1 or t.stride(0) >= Q * k)
+        return t if ok else t.contiguous()
+    scores = dense_lists(scores, torch.float32)
+    idx = dense_lists(idx, torch.int32)
+    if G > 1 and scores.stride(0) != idx.stride(0):
+        scores, idx = scores.contiguous(), idx.contiguous()
     out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((Q, k_out), dtype=torch.int32, device=scores.device)
     if Q == 0:
         return out_s, out_i
-    rc = lib.cir_topk_merge(_lib.ptr(scores), _lib.ptr(idx), G, Q, k, _lib.ptr(out_s), _lib.ptr(out_i), k_out,
+    g_stride = scores.stride(0) if G > 1 else Q * k
+    rc = lib.cir_topk_merge(_lib.ptr(scores), _lib.ptr(idx), G, Q, k, g_stride, _lib.ptr(out_s), _lib.ptr(out_i), k_out,
                             _lib.stream_of(scores))
     _lib.check(rc, "cir_topk_merge")
     return out_s, out_i

@@ -52,6 +52,7 @@ struct SelParams {
     const float* in_scores;
     const int32_t* in_idx;
     int kin;
+    long long g_stride;   // elements between consecutive lists of one query set
     int G, Q, k;
     float* out_scores;
     int32_t* out_idx;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
                     const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
                     for (int t = lane; t < c; t += 32) buf[dst + t] = raw_to_key(__ldcg(L + t));
                 } else {
-                    const size_t o = ((size_t)(g0 + g) * p.Q + q) * p.kin;
+                    const size_t o = (size_t)(g0 + g) * (size_t)p.g_stride + (size_t)q * p.kin;
                     for (int t = lane; t < c; t += 32) {
                         const int32_t ix = __ldg(p.in_idx + o + t);
                         buf[dst + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
@@ -436,15 +437,17 @@ static long long sort_npad(long long N) {
 
 using namespace cir;
 
-extern "C" int cir_topk_merge(const float* scores, const int32_t* idx, int G, int Q, int k, float* out_scores,
-                              int32_t* out_idx, int k_out, void* stream) {
+extern "C" int cir_topk_merge(const float* scores, const int32_t* idx, int G, int Q, int k, int64_t g_stride,
+                              float* out_scores, int32_t* out_idx, int k_out, void* stream) {
     CIR_REQUIRE(scores && idx && out_scores && out_idx, CIR_ERR_INVALID_ARG, "cir_topk_merge: null pointer");
     CIR_REQUIRE(G >= 1 && Q >= 0 && k >= 1 && k_out >= 1, CIR_ERR_INVALID_ARG, "cir_topk_merge: bad shape");
     CIR_REQUIRE(k_out + k <= SEL_N && k_out <= SEL_MAX_KOUT, CIR_ERR_UNSUPPORTED,
                 "cir_topk_merge: k_out + k = %d exceeds %d (or k_out > %d)", k_out + k, SEL_N, SEL_MAX_KOUT);
     if (Q == 0) return CIR_OK;
     SelParams p{};
+    CIR_REQUIRE(g_stride == 0 || g_stride >= (int64_t)Q * k, CIR_ERR_INVALID_ARG, "cir_topk_merge: g_stride too small");
     p.in_scores = scores; p.in_idx = idx; p.kin = k;
+    p.g_stride = g_stride ? g_stride : (long long)Q * k;
     p.G = G; p.Q = Q; p.k = k_out;
     p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = k_out; p.idx_offset = 0;
     return launch_select<1>(p, Q, static_cast<cudaStream_t>(stream));

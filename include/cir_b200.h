@@ -143,8 +143,9 @@ int cir_sort_rows_desc(const float* scores, int Q, int64_t N, int64_t ld,
 /* merge G sorted top-k lists per query (shards of one GPU or the all-gathered lists of G
  * GPUs) into one: in [G, Q, k] -> out [Q, k_out], k_out <= k*G.  Exact:
  * top-k(union of shard top-k) == top-k(global).  Entries with idx < 0 are ignored;
- * k_out + k <= 4096. */
-int cir_topk_merge(const float* scores, const int32_t* idx, int G, int Q, int k,
+ * k_out + k <= 4096, k_out <= 1024.  g_stride = elements between list g and list g + 1 (0 = Q * k, dense);
+ * an all-gathered buffer that interleaves scores and indices per rank is merged in place with g_stride = 2 Q k. */
+int cir_topk_merge(const float* scores, const int32_t* idx, int G, int Q, int k, int64_t g_stride,
                    float* out_scores, int32_t* out_idx, int k_out, void* stream);
 
 /* exact fp32 re-scoring of candidate lists and final ordering:

@@ -142,6 +142,14 @@ def test_merge_equals_global_topk():
     ms, mi = S.merge_topk(torch.stack(parts_s), torch.stack(parts_i), 50)
     assert torch.equal(mi, i_ref)
     assert torch.equal(ms, s_ref)
+    # the all-gathered exchange buffer [G, 2, Q, k] (scores and indices interleaved per rank) merges in place
+    G = len(parts_s)
+    buf = torch.empty((G, 2, 65, 50), dtype=torch.int32, device=DEV)
+    for r in range(G):
+        buf[r, 0] = parts_s[r].view(torch.int32)
+        buf[r, 1] = parts_i[r]
+    ms2, mi2 = S.merge_topk(buf[:, 0].view(torch.float32), buf[:, 1], 50)
+    assert torch.equal(mi2, i_ref) and torch.equal(ms2, s_ref)
 
 
 def test_many_splits_small_k_large_n():
