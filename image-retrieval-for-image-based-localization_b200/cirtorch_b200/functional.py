@@ -88,16 +88,85 @@ def _tail_reference_formula(x, p, eps, weight, bias, pooling, flags, l2_eps):
     return v
 
 
+def _gem_bwd_launch(x, p, eps, g, dg, want_dx, want_s):
+    """cir_gem_bwd: the N*C*H*W-sized part of the backward (one read of x, one write of dx)."""
+    lib = _lib.load()
+    N, Cc, H, W = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    S = torch.empty((N, Cc), dtype=torch.float32, device=x.device) if want_s else None
+    pc = p.detach().reshape(-1).float().contiguous()
+    rc = lib.cir_gem_bwd(_lib.ptr(x), N, Cc, H, W, _lib.ptr(pc), 0 if pc.numel() == 1 else 1, float(eps),
+                         _lib.ptr(g), _lib.ptr(dg), _lib.ptr(dx), _lib.ptr(S), _lib.stream_of(x))
+    _lib.check(rc, "cir_gem_bwd")
+    return dx, S
+
+
+def _l2n_bwd(v, gout, l2_eps):
+    """Gradient of v / (||v|| + eps) w.r.t. v (rows)."""
+    s = v.norm(p=2, dim=1, keepdim=True)
+    return gout / (s + l2_eps) - v * ((v * gout).sum(dim=1, keepdim=True) / (s * (s + l2_eps) ** 2))
+
+
 class _TailFn(torch.autograd.Function):
+    """Forward = the fused CUDA kernel.  Backward for GeM pooling: the [N, C] / [N, D]-sized chain (two L2Ns, the
+    Linear) in stock torch ops + cuBLAS, and ONE streaming kernel (cir_gem_bwd) for everything that touches the
+    feature map: dx and the sum needed for dL/dp.  MAC / SPoC recompute the tail with differentiable torch ops."""
+
     @staticmethod
     def forward(ctx, x, p, weight, bias, eps, pooling, flags, l2_eps):
         ctx.cfg = (eps, pooling, flags, l2_eps)
-        ctx.save_for_backward(x, p, weight, bias)
-        return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
+        xc = _as_f32_contig(x)
+        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
+        g = None
+        if pooling in ("GeM", "GeMmp") and out.shape[0] > 0:
+            N, Cc = xc.shape[0], xc.shape[1]
+            if flags & CIR_TAIL_POOL_ONLY:
+                g = out
+            else:   # the kernel left the pooled values at the head of its workspace: keep a copy (N*C*4 bytes)
+                ws = _lib.workspace(xc.device, 0, "tail")
+                g = ws[:N * Cc * 4].view(torch.float32).view(N, Cc).clone()
+        ctx.save_for_backward(xc, p, weight, bias, g)
+        return out
 
     @staticmethod
-    def backward(ctx, g):
-        x, p, weight, bias = ctx.saved_tensors
+    def backward(ctx, gout):
+        x, p, weight, bias, g = ctx.saved_tensors
+        eps, pooling, flags, l2_eps = ctx.cfg
+        need = ctx.needs_input_grad
+        if g is None:
+            return _TailFn._backward_recompute(ctx, gout)
+        gout = gout.contiguous().float()
+        dW = db = None
+        with torch.no_grad():
+            if flags & CIR_TAIL_POOL_ONLY:
+                dg = gout
+            elif flags & CIR_TAIL_NO_WHITEN:
+                dg = _l2n_bwd(g, gout, l2_eps)
+            else:
+                s = g.norm(p=2, dim=1, keepdim=True)
+                u = g / (s + l2_eps)
+                z = torch.nn.functional.linear(u, weight, bias)
+                dz = _l2n_bwd(z, gout, l2_eps)
+                if need[2]:
+                    dW = dz.t() @ u
+                if bias is not None and need[3]:
+                    db = dz.sum(dim=0)
+                dg = _l2n_bwd(g, dz @ weight, l2_eps)
+            dx = dp = None
+            if need[0] or need[1]:
+                dx, S = _gem_bwd_launch(x, p, eps, g, dg.contiguous(), need[0], need[1])
+                if need[1]:
+                    pp = p.detach().reshape(1, -1).float()
+                    HW = x.shape[2] * x.shape[3]
+                    # d g / d p = g * ( -ln(g) / p + S / (p * HW * g^p) ),  g^p = mean t^p
+                    dgdp = g * (-torch.log(g) / pp + S / (pp * HW * g.pow(pp)))
+                    dp_full = (dg * dgdp)
+                    dp = dp_full.sum().reshape(p.shape) if p.numel() == 1 else dp_full.sum(dim=0).reshape(p.shape)
+        return dx, dp, dW, db, None, None, None, None
+
+    @staticmethod
+    def _backward_recompute(ctx, g):
+        x, p, weight, bias, _ = ctx.saved_tensors
         eps, pooling, flags, l2_eps = ctx.cfg
         ins = []
         with torch.enable_grad():

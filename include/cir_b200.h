@@ -80,6 +80,13 @@ int cir_tail_fwd(const float* x, int N, int C, int H, int W,
                  float* out, int out_ld,
                  void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
+/* Backward of the GeM pooling over the feature map (training, scripts/train_globalF.py:480-488; the autograd of
+ * pools.py:37-38): dx[n,c,:,:] = dg[n,c] * g[n,c]^(1-p) * max(x,eps)^(p-1) / (H W) where x >= eps, and, when S != NULL,
+ * S[n,c] = sum_hw max(x,eps)^p ln max(x,eps) (for dL/dp).  g = the forward's pooled values [N, C], dg = their gradient.
+ * One pass over x (read) and dx (write); everything else of the tail's backward is [N, C]-sized. */
+int cir_gem_bwd(const float* x, int N, int C, int H, int W, const float* p, int p_stride, float eps_gem,
+                const float* g, const float* dg, float* dx, float* S, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * 2. Bias + L2N of projected descriptors
  *    replaces the tail of whitenapply   cirtorch/utils/whiten.py:8-12

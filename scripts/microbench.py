@@ -39,6 +39,27 @@ if what in ("all", "tail"):
     ]:
         ms = timeit(fn)
         print(f"tail {name:22s} {ms*1e3:8.1f} us  {gb/ms:8.1f} GB/s(x only)")
+if what in ("all", "bwd"):
+    from cirtorch_b200.functional import _gem_bwd_launch
+    B, C, H, W = 64, 2048, 32, 32
+    x = torch.relu(torch.randn((B, C, H, W), device=dev))
+    g = torch.rand((B, C), device=dev) + 0.1
+    dg = torch.randn((B, C), device=dev)
+    for pv in (3.0, 2.7):
+        pt = torch.full((1,), pv, device=dev)
+        for want_s in (False, True):
+            ms = timeit(lambda: _gem_bwd_launch(x, pt, 1e-6, g, dg, True, want_s), n=10)
+            print(f"gem_bwd p={pv} dp={want_s}: {ms*1e3:8.1f} us  {2*B*C*H*W*4/ms/1e6:8.1f} GB/s (read x + write dx)")
+    from cirtorch_b200.modules.heads.global_head import globalHead
+    head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=2048).to(dev)
+    xg = x.clone().requires_grad_(True)
+    tgt = torch.randn(2048, B, device=dev)
+    def fb():
+        out = head(xg)
+        (out * tgt).sum().backward()
+        xg.grad = None
+    ms = timeit(fb, n=10)
+    print(f"globalHead forward + backward (x, p, W, b grads): {ms*1e3:8.1f} us")
 if what in ("all", "tail", "stamps"):
     import ctypes as C
     from cirtorch_b200 import _lib

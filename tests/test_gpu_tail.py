@@ -130,6 +130,54 @@ def test_gradients_match_autograd():
         np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=2e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("pooling,p,mode", [("GeM", 3.0, "full"), ("GeM", 2.5, "nowhiten"), ("GeMmp", 3.0, "full"),
+                                            ("GeM", 2.2, "pool"), ("MAC", None, "full")])
+def test_gradients_all_modes(pooling, p, mode):
+    """cir_gem_bwd + the [N, C]-sized chain vs autograd of the oracle formula, every mode of the tail."""
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(5)
+    x = torch.relu(torch.randn(5, 64, 6, 8)) + 0.02
+    x[0, 0] = 0.0                       # a fully clamped row: zero gradient, finite dp
+    head = _head(64, pooling, p=p if p else 3.0)
+    if pooling == "GeMmp":
+        with torch.no_grad():
+            head.pool.p.copy_(torch.linspace(2.0, 4.0, 64))
+    pt = getattr(head.pool, "p", None)
+
+    def run(xin, pp, W, b, device):
+        kw = dict(p=pp, eps=1e-6, weight=W, bias=b, pooling=pooling)
+        if device == "ref":
+            if mode == "pool":
+                return O.gem(xin, pp).flatten(1)
+            return O.head_forward(xin, pp, 1e-6, W, b, do_whitening=(mode == "full"), pooling=pooling).t()
+        return LF.descriptor_tail(xin, do_whitening=(mode == "full"), pool_only=(mode == "pool"), **kw)
+
+    xr = x.clone().requires_grad_(True)
+    ref = run(xr, pt, head.whiten.weight, head.whiten.bias, "ref")
+    tgt = torch.randn_like(ref)
+    (ref * tgt).sum().backward()
+    gref = {"x": xr.grad.clone()}
+    if pt is not None:
+        gref["p"] = pt.grad.clone()
+    if mode == "full":
+        gref["W"], gref["b"] = head.whiten.weight.grad.clone(), head.whiten.bias.grad.clone()
+    head.zero_grad()
+    head = head.to(DEV)
+    pt = getattr(head.pool, "p", None)
+    xg = x.to(DEV).requires_grad_(True)
+    out = run(xg, pt, head.whiten.weight, head.whiten.bias, "dev")
+    (out * tgt.to(DEV)).sum().backward()
+    got = {"x": xg.grad}
+    if pt is not None:
+        got["p"] = pt.grad
+    if mode == "full":
+        got["W"], got["b"] = head.whiten.weight.grad, head.whiten.bias.grad
+    for k in gref:
+        scale = float(gref[k].abs().max()) + 1e-12
+        err = float((got[k].cpu() - gref[k]).abs().max()) / scale
+        assert err < 2e-3, (k, err)
+
+
 def test_cpu_tensor_is_rejected():
     from cirtorch_b200._lib import CirError
     head = _head(16)
