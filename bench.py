@@ -284,11 +284,35 @@ def bench_search(dev, rank, world, pk, steps, warmup):
         qp = S.pack_rows(q32, "query", "bf16")
 
         both, views = P.topk_exchange_buffer(Q, TOPK, dev)
+        shard = None
+        exchange = "none" if world == 1 else "nccl all_gather"
+        if world > 1:
+            # fused exchange: the selection kernel stores the lists into every peer's buffer over NVLink
+            try:
+                shard = P.ShardedIndex.__new__(P.ShardedIndex)
+                shard._exchange, shard.group, shard.rank, shard.world_size, shard.lo, shard.hi, shard.n_global = \
+                    {}, None, rank, world, lo, hi, DB_N
+                idx_obj = S.Index.__new__(S.Index)
+                idx_obj.mode, idx_obj.N, idx_obj.D, idx_obj.row_offset, idx_obj.packed, idx_obj.rows32, idx_obj.labels = \
+                    "bf16", n_loc, DB_D, lo, dbp, rows32, None
+                shard.index = idx_obj
+                shard.search_packed_p2p(qp, TOPK)
+                torch.cuda.synchronize()
+                exchange = "peer stores over NVLink fused into the selection kernel (symmetric memory)"
+            except Exception as e:  # noqa: BLE001  (no symmetric memory on this box: NCCL all_gather instead)
+                shard = None
+                exchange = "nccl all_gather (%s)" % type(e).__name__
+            flag = torch.tensor([1 if shard is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                shard = None
 
         def step_local():
             return S.search_packed(qp, dbp, TOPK, idx_offset=lo, out=views)
 
         def step():
+            if shard is not None:
+                return shard.search_packed_p2p(qp, TOPK)
             s, i = step_local()
             if world > 1:
                 s_all, i_all = P.gather_topk(s, i, both=both)
@@ -302,7 +326,8 @@ def bench_search(dev, rank, world, pk, steps, warmup):
         ms_kernel = timed_region(step_local, k_steps, 3, world) / k_steps
         flops = 2.0 * Q * n_loc * DB_D
         res = {"queries_per_s": Q / (ms * 1e-3), "ms_per_search": ms, "ms_local_kernels": ms_kernel,
-               "steps": k_steps, "launches_per_search": launches // (k_steps + max(3, warmup)), "Q": Q, "N": DB_N, "k": TOPK}
+               "steps": k_steps, "launches_per_search": launches // (k_steps + max(3, warmup)), "Q": Q, "N": DB_N, "k": TOPK,
+               "exchange": exchange}
         if Q >= 1000:
             tf = flops / (ms_kernel * 1e-3) / 1e12
             res["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",

@@ -36,6 +36,8 @@ SIGNATURES = {
     "cir_search_workspace_bytes": (_c_int, [_c_int, _c_i64, _c_int, _c_int, _szp]),
     "cir_search_topk": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp,
                                  C.c_int32, _vp, C.c_size_t, C.c_uint, _vp]),
+    "cir_search_topk_exchange": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, C.c_int32, C.POINTER(C.c_void_p), _c_int,
+                                          _c_int, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_scores_dense": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _c_i64, _vp]),
     "cir_sort_rows_workspace_bytes": (_c_int, [_c_int, _c_i64, _szp]),
     "cir_sort_rows_desc": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, C.c_size_t, _vp]),

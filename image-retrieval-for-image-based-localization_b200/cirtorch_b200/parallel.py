@@ -50,11 +50,41 @@ def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None, both: torch
     return out[:, 0].view(torch.float32), out[:, 1]
 
 
+class PeerExchange:
+    """NVLink exchange buffers for the fused search + all-gather (cir_search_topk_exchange).
+
+    Two symmetric-memory buffers [G][2][Q][k] (int32 words) per rank, used alternately: the final selection kernel of
+    every rank stores its lists straight into slot `rank` of all peers' buffers; one device-side barrier later every
+    rank merges its own buffer.  Double buffering makes the single barrier per search sufficient (a rank can only
+    reach the barrier of search i+1 after it launched the merge of search i)."""
+
+    def __init__(self, Q: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world_size = world(group)
+        self.Q, self.k = Q, k
+        self.bufs, self.handles, self.ptrs = [], [], []
+        import ctypes as C
+        for _ in range(2):
+            t = symm_mem.empty((self.world_size, 2, Q, k), dtype=torch.int32, device=device)
+            h = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptrs.append((C.c_void_p * self.world_size)(*[int(a) for a in h.buffer_ptrs]))
+        self.turn = 0
+
+    def next(self):
+        i = self.turn
+        self.turn ^= 1
+        return self.bufs[i], self.handles[i], self.ptrs[i]
+
+
 class ShardedIndex:
     """Row-sharded database: this rank holds rows [lo, hi) of a global N-row database."""
 
     def __init__(self, local_rows: torch.Tensor, n_global: int, group=None, mode="bf16", keep_fp32=True):
         from .search import Index
+        self._exchange = {}
         self.group = group
         self.rank, self.world_size = world(group)
         self.lo, self.hi = shard_bounds(n_global, self.world_size, self.rank)
@@ -74,6 +104,29 @@ class ShardedIndex:
             return s, i
         s_all, i_all = gather_topk(s, i, self.group)
         return merge_topk(s_all, i_all, k)      # strided views of the gathered buffer, merged in place
+
+    def search_packed_p2p(self, qp, k):
+        """Global top-k of packed queries with the exchange fused into the search: every rank's selection kernel
+        writes its lists into all peers' buffers over NVLink, one device barrier, local merge.  No NCCL call."""
+        import ctypes as C
+        from . import _lib
+        from .search import merge_topk
+        lib = _lib.load()
+        Q, Kd = qp.shape
+        key = (Q, k)
+        ex = self._exchange.get(key)
+        if ex is None:
+            ex = self._exchange[key] = PeerExchange(Q, k, qp.device, self.group)
+        buf, handle, ptrs = ex.next()
+        need = C.c_size_t(0)
+        _lib.check(lib.cir_search_workspace_bytes(Q, self.index.N, Kd, k, C.byref(need)), "cir_search_workspace_bytes")
+        ws = _lib.workspace(qp.device, need.value, "search")
+        rc = lib.cir_search_topk_exchange(_lib.ptr(qp), Q, _lib.ptr(self.index.packed), self.index.N, Kd, k, self.lo,
+                                          ptrs, self.world_size, self.rank, _lib.ptr(ws), ws.numel(), 0,
+                                          _lib.stream_of(qp))
+        _lib.check(rc, "cir_search_topk_exchange")
+        handle.barrier()                                    # device-side, on the current stream
+        return merge_topk(buf[:, 0].view(torch.float32), buf[:, 1], k)
 
 
 def extract_vectors_dp(net, images, group=None, **kw):

@@ -14,6 +14,7 @@
 
 namespace cir {
 
+constexpr int SEL_MAX_PEERS = 16;
 constexpr int SEL_N = 4096;
 constexpr int SEL_THREADS = 512;
 
@@ -58,6 +59,10 @@ struct SelParams {
     int32_t* out_idx;
     int out_ld;
     int32_t idx_offset;
+    // fused exchange: the final lists are also stored into every peer GPU's exchange buffer [G][2][Q][k] (32-bit words:
+    // scores then indices of rank g) through NVLink-mapped pointers -- an all-gather without a separate collective
+    int n_peers, my_rank;
+    void* peer[SEL_MAX_PEERS];
 };
 
 constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
@@ -217,8 +222,18 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
     for (int t = tid; t < p.k; t += SEL_THREADS) {
         const unsigned long long key = t < fill ? buf[t] : 0ull;
         const bool ok = key != 0ull;
-        p.out_scores[(size_t)q * p.out_ld + t] = ok ? key_score(key) : -INFINITY;
-        p.out_idx[(size_t)q * p.out_ld + t] = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
+        const float sc = ok ? key_score(key) : -INFINITY;
+        const int32_t ix = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
+        if (p.out_scores) {
+            p.out_scores[(size_t)q * p.out_ld + t] = sc;
+            p.out_idx[(size_t)q * p.out_ld + t] = ix;
+        }
+        for (int g = 0; g < p.n_peers; ++g) {
+            // peer buffer layout [G][2][Q][k]; this rank fills slot my_rank of every peer (plain stores over NVLink)
+            uint32_t* base = static_cast<uint32_t*>(p.peer[g]) + (size_t)p.my_rank * 2 * p.Q * p.k;
+            base[(size_t)q * p.k + t] = __float_as_uint(sc);
+            base[(size_t)p.Q * p.k + (size_t)q * p.k + t] = (uint32_t)ix;
+        }
     }
 }
 
@@ -310,12 +325,16 @@ static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
 }
 
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
-                             float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream) {
+                             float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream,
+                             void* const* peers, int n_peers, int my_rank) {
     CIR_REQUIRE(k + cap <= SEL_N, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_N);
     SelParams p{};
     p.lists = lists; p.counts = counts; p.Qpad = Qpad; p.cap = cap;
     p.G = S; p.Q = Q; p.k = k;
     p.out_scores = out_scores; p.out_idx = out_idx; p.out_ld = out_ld; p.idx_offset = idx_offset;
+    CIR_REQUIRE(n_peers >= 0 && n_peers <= SEL_MAX_PEERS, CIR_ERR_UNSUPPORTED, "topk select: at most %d peers", SEL_MAX_PEERS);
+    p.n_peers = n_peers; p.my_rank = my_rank;
+    for (int g = 0; g < n_peers; ++g) p.peer[g] = peers[g];
     return launch_select<0>(p, Q, stream);
 }
 

@@ -135,6 +135,15 @@ int cir_search_topk(const void* q, int Q, const void* db, int64_t N, int Kd, int
                     float* out_scores, int32_t* out_idx, int32_t idx_offset,
                     void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
+/* Sharded search with the exchange fused into the final selection: instead of returning its lists, rank `my_rank`
+ * stores them into slot `my_rank` of EVERY peer's exchange buffer -- peer_bufs[g] is a device pointer (mapped into
+ * this process, e.g. by torch symmetric memory / CUDA IPC over NVLink) to an int32 buffer [n_peers][2][Q][k]
+ * (fp32 score bits, then indices).  After a cross-GPU barrier every rank merges its own buffer with
+ * cir_topk_merge(scores = buf, idx = buf + Q*k, G = n_peers, g_stride = 2*Q*k).  peer_bufs is a HOST array. */
+int cir_search_topk_exchange(const void* q, int Q, const void* db, int64_t N, int Kd, int k, int32_t idx_offset,
+                             void* const* peer_bufs, int n_peers, int my_rank,
+                             void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
 /* dense scores through the same GEMM (the reference's full `scores` matrix, for full
  * ranking of small databases): out [Q, ld_out] fp32, out[q, n] = q . db[n] */
 int cir_scores_dense(const void* q, int Q, const void* db, int64_t N, int Kd,

@@ -1,0 +1,59 @@
+"""Two-GPU NCCL / NVLink tests of the sharded search (skipped on a single-GPU box):
+NCCL all_gather path and the fused peer-store exchange must both equal the single-GPU result."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "image-retrieval-for-image-based-localization_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from cirtorch_b200 import parallel as P, search as S
+    g = torch.Generator(device="cpu").manual_seed(0)
+    N, D, Q, k = 70_001, 256, 300, 50
+    db = torch.randn((N, D), generator=g)
+    db = (db / db.norm(dim=1, keepdim=True)).to(dev)
+    q = torch.randn((Q, D), generator=g)
+    q = (q / q.norm(dim=1, keepdim=True)).to(dev)
+    s_ref, i_ref = S.search_topk_rows(q, db, k, mode="bf16", rescore=False)
+    lo, hi = P.shard_bounds(N, world, rank)
+    sh = P.ShardedIndex(db[lo:hi].contiguous(), N, mode="bf16")
+    s1, i1 = sh.search_rows(q, k, rescore=False)                      # NCCL all_gather + merge
+    ok = bool(torch.equal(i1, i_ref)) and bool(torch.equal(s1, s_ref))
+    qp = S.pack_rows(q, "query", "bf16")
+    for _ in range(3):                                               # alternates the two exchange buffers
+        s2, i2 = sh.search_packed_p2p(qp, k)                         # fused peer-store exchange
+        ok = ok and bool(torch.equal(i2, i_ref)) and bool(torch.equal(s2, s_ref))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    if rank == 0:
+        out.put(int(flag))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_search_nccl_and_p2p():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 1
