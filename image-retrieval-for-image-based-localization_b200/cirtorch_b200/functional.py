@@ -124,7 +124,11 @@ class _TailFn(torch.autograd.Function):
                 g = out
             else:   # the kernel left the pooled values at the head of its workspace: keep a copy (N*C*4 bytes)
                 ws = _lib.workspace(xc.device, 0, "tail")
-                g = ws[:N * Cc * 4].view(torch.float32).view(N, Cc).clone()
+                if flags & CIR_TAIL_NO_WHITEN:
+                    g = ws[:N * Cc * 4].view(torch.float32).view(N, Cc).clone()
+                else:   # whitening: stored as bf16 hi + lo parts ([N, C] each), g = hi + lo
+                    hl = ws[:N * Cc * 4].view(torch.bfloat16).view(2, N, Cc)
+                    g = hl[0].float() + hl[1].float()
         ctx.save_for_backward(xc, p, weight, bias, g)
         return out
 

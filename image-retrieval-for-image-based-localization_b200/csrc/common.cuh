@@ -1,6 +1,7 @@
 // Shared host/device helpers for libcir_b200.so (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -22,6 +23,10 @@ struct DeviceInfo {
     int coop = 0;
 };
 const DeviceInfo& device_info();   // cached per calling thread's current device
+
+// K-major bf16 matrix [rows, cols] with row pitch `pitch_elems` -> TMA map with box {64 cols, box_rows},
+// 128 B swizzle, zero fill out of bounds (cuTensorMapEncodeTiled through the runtime's driver entry point)
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows);
 
 #define CIR_CHECK_CUDA(expr)                                                              \
     do {                                                                                  \

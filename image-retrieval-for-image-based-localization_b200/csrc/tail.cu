@@ -12,20 +12,24 @@
 //            output rows, <= 128 KB) is prefetched into shared memory with cp.async.
 //            Rows that TMA cannot move (H*W % 4 != 0, > 16 KB, unaligned) take a direct-load path.
 //   barrier  cooperative grid sync
-//   phase B  CTA i owns a slice of <= 16 output dims.  Y[64 x 16] = G[64 x K] . Wslice^T on
-//            mma.sync m16n8k16 bf16 with every fp32 operand split into hi + lo bf16
-//            (hi.hi + hi.lo + lo.hi, fp32 accumulate: ~1e-5 relative, inside the 1e-4 bar).
-//            16 warps = 2 image halves x 8 K ranges; A fragments are loaded straight from the
-//            L2-resident pooled vectors (one full 128 B line per 4 lanes, next block
-//            prefetched), B fragments from the shared-memory W slice; a shared-memory
-//            reduction over the K ranges; the first L2N is folded in as a scale.
-//   barrier  cooperative grid sync (per-chunk partial sums of squares)
-//   phase C  second L2N: partial sums added in a fixed order (deterministic), outputs rescaled.
+//            Phase A stores the pooled vectors already split into bf16 hi + lo parts.
+//   phase B  split-K projection on tcgen05: unit (nt, ks) = 128 output dims x a 256-wide K slice;
+//            part[ks][n][nt*128 ..] = G[128 images x 256] . W_tile^T with every fp32 operand split into
+//            hi + lo bf16 (hi.hi + hi.lo + lo.hi, fp32 accumulator in TMEM: ~1e-5 relative, inside
+//            the 1e-4 bar).  A CTA reads only ITS K slice of the pooled vectors (64 KB by TMA, 128 B
+//            swizzle) instead of all of them; its W tile (128 KB as bf16 hi / lo UMMA tiles) was
+//            converted during phase A by the idle lanes of the producer warp.  Warp 0 TMA, warp 1
+//            MMA issue, warp 2 TMEM alloc, warps 8-11 epilogue (tcgen05.ld -> partial sums).
+//   barrier  cooperative grid sync
+//   phase C  one CTA per image: adds the K-slice partial sums in a fixed order (deterministic), applies
+//            the first L2N as a scale (||g|| from the pooled vector), the bias and the second L2N.
 //
 // Algorithmic HBM bytes per launch: N*C*H*W*4 (x) + D_out*C*4 (W) + D_out*4 (b) + N*D_out*4 (out).
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <string.h>
+#include <type_traits>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -36,14 +40,15 @@ using namespace ptx;
 constexpr int TAIL_THREADS = 512;
 constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 consume, warp 15 produces
-constexpr int TAIL_JMAX = 16;                        // output dims per phase-B chunk (two n8 MMA tiles)
-constexpr int TAIL_KC = 2048;                        // K extent of the W slice staged in shared memory
+constexpr int TAIL_NT = 128;                         // output dims per projection unit (UMMA N)
+constexpr int TAIL_KS = 256;                         // K slice per projection unit (4 k blocks of 64)
 constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows, <= 16 KB
 constexpr int TAIL_MAX_SLOTS = 8;
-constexpr int TAIL_MB = 64;                          // images per phase-B pass
+constexpr int TAIL_MAX_BARS = 32;
+constexpr int TAIL_MB = 128;                         // images per phase-B pass (UMMA M)
+constexpr int TAIL_BT_BYTES = TAIL_NT * 128;         // one B tile: 128 rows x 64 k bf16, 128 B swizzle (16 KB)
+constexpr int TAIL_W_BYTES = (TAIL_KS / 64) * 2 * TAIL_BT_BYTES;   // hi + lo tiles of a unit's W tile: 128 KB
 constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;    // debug time stamps: up to 1024 CTAs x 8 slots
-// phase-B reduction scratch (aliases the ring): [8 K ranges][8 tile combos][32 lanes][4] + [8][64] + [64][16] + [64]
-constexpr int TAIL_RED_FLOATS = 8 * 8 * 32 * 4 + 8 * TAIL_MB + TAIL_MB * TAIL_JMAX + TAIL_MB;
 
 struct TailParams {
     const float* x;
@@ -57,10 +62,12 @@ struct TailParams {
     int D_out;
     float* out;
     int out_ld;
-    float* pooled;     // [N, pooled_ld]
+    float* pooled;     // [N, pooled_ld] fp32 (pool-only / no-whiten modes)
     int pooled_ld;
-    float* partial;    // [n_chunks, N] sums of squares of the un-normalised outputs
-    int jch, n_chunks;
+    __nv_bfloat16* pooled_hi;   // whiten mode: pooled vectors as bf16 hi + lo parts, [N, C] each (same bytes as fp32)
+    __nv_bfloat16* pooled_lo;
+    float* part;       // [n_kslices][N][D_out] partial projections of the K slices
+    int n_ntiles, n_kslices, units;   // projection units: u = ks * n_ntiles + nt
     unsigned flags;
     int bulk_ok;       // rows can be moved by cp.async.bulk
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
@@ -200,6 +207,19 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = pack_bf16x2(a - __low2float(h), b - __high2float(h));
 }
+// sum of squares of 8 values given as packed bf16 pairs of hi parts and of lo parts (value = hi + lo)
+__device__ __forceinline__ float sumsq8(const uint4& h, const uint4& l) {
+    float s = 0.0f;
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+        const float b = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+    }
+    return s;
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -207,13 +227,72 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailParams P) {
-    extern __shared__ __align__(128) unsigned char tail_smem[];
-    float* Ws = reinterpret_cast<float*>(tail_smem);                               // [jch][TAIL_KC]
+// fp32 W tile of projection unit u = (nt, ks) -> bf16 hi / lo UMMA B tiles (K-major, 128 B swizzle):
+// tile (kb, part) at Bt + (kb * 2 + part) * 16 KB, row r at (r / 8) * 1024 + (r % 8) * 128, 16-byte chunk c at
+// ((c ^ (r % 8)) * 16).  One task = one chunk (8 consecutive k of one row); rows >= D_out and k >= C become zeros.
+// BATCH tasks are loaded before any is converted, so a lane has 2 * BATCH 16-byte loads in flight.
+constexpr int TAIL_W_TASKS = TAIL_NT * (TAIL_KS / 8);         // 4096 chunks per W tile
+
+// tasks t0, t0 + nworkers, ... (at most max_batches * BATCH of them)
+template <int BATCH>
+__device__ __forceinline__ void convert_w_tile(const TailParams& P, unsigned char* Bt, int unit, int worker, int nworkers,
+                                               int first_batch = 0, int max_batches = 1 << 30) {
+    const int nt = unit % P.n_ntiles, ks = unit / P.n_ntiles;
+    const int j0 = nt * TAIL_NT, k0 = ks * TAIL_KS;
+    constexpr int tasks = TAIL_W_TASKS;
+    int nb = 0;
+    for (int t0 = worker + first_batch * nworkers * BATCH; t0 < tasks && nb < max_batches; t0 += nworkers * BATCH, ++nb) {
+        float4 w0[BATCH], w1[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int t = t0 + u * nworkers;
+            const int r = t >> 5, c8 = t & 31;
+            const int j = j0 + r, k = k0 + c8 * 8;
+            w0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w1[u] = w0[u];
+            if (t < tasks && j < P.D_out && k < P.C) {
+                const float* w = P.Wt + (size_t)j * P.C + k;
+                w0[u] = __ldg(reinterpret_cast<const float4*>(w));
+                w1[u] = __ldg(reinterpret_cast<const float4*>(w + 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int t = t0 + u * nworkers;
+            if (t < tasks) {
+                const int r = t >> 5, c8 = t & 31;
+                const int kb = c8 >> 3, c = c8 & 7;
+                uint4 hi, lo;
+                split2(w0[u].x, w0[u].y, hi.x, lo.x);
+                split2(w0[u].z, w0[u].w, hi.y, lo.y);
+                split2(w1[u].x, w1[u].y, hi.z, lo.z);
+                split2(w1[u].z, w1[u].w, hi.w, lo.w);
+                unsigned char* dst = Bt + (size_t)(kb * 2) * TAIL_BT_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + TAIL_BT_BYTES) = lo;
+            }
+        }
+    }
+    fence_proxy_async();       // the tiles are read by the tensor core (async proxy)
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
+tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, const TailParams P) {
+    extern __shared__ __align__(1024) unsigned char tail_smem_raw[];
+    unsigned char* tail_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* Bt = tail_smem;                                                 // W slice as UMMA B tiles (whiten)
     unsigned char* ring = tail_smem + P.w_bytes;                                   // [n_slots][16 KB]
-    float* red = reinterpret_cast<float*>(ring);                                   // phase B scratch (aliases the ring)
-    __shared__ __align__(8) uint64_t full_bar[TAIL_MAX_SLOTS];
-    __shared__ __align__(8) uint64_t empty_bar[TAIL_MAX_SLOTS];
+    // Phase A barriers: a ring of nbar = M * n_slots (full, empty) pairs over the n_slots data slots.  A consumer warp
+    // only visits the slots that hold its rows, so it does not observe every phase of a barrier; with a single ring a
+    // parity wait could then be satisfied by an OLDER, still incomplete phase (bulk copies complete out of order).
+    // With (M - 1) * n_slots >= the largest gap between two rows of a warp, the previous use of a barrier is complete
+    // before anyone waits for its next use.
+    __shared__ __align__(8) uint64_t full_bar[TAIL_MAX_BARS];
+    __shared__ __align__(8) uint64_t empty_bar[TAIL_MAX_BARS];
+    __shared__ __align__(8) uint64_t fullB[TAIL_MAX_SLOTS];      // phase B ring: TMA -> MMA / sum-of-squares warps
+    __shared__ __align__(8) uint64_t emptyB[TAIL_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t accB;                       // accumulator complete
+    __shared__ uint32_t tmem_slot;
     cg::grid_group grid = cg::this_grid();
 
     const int tid = threadIdx.x;
@@ -222,25 +301,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
     const bool pool_only = (P.flags & CIR_TAIL_POOL_ONLY) != 0;
     const bool whiten = !pool_only && !(P.flags & CIR_TAIL_NO_WHITEN);
 
-    auto stage_W = [&](int chunk, int kc0) {
-        const int j0 = chunk * P.jch;
-        const int J = min(P.jch, P.D_out - j0);
-        const int kw = min(TAIL_KC, P.C - kc0);
-        const int nvr = kw >> 2;
-        for (int i = tid; i < J * nvr; i += TAIL_THREADS) {
-            const int j = i / nvr, kv = i - j * nvr;
-            cp_async16(&Ws[j * TAIL_KC + kv * 4], P.Wt + (size_t)(j0 + j) * P.C + kc0 + kv * 4);
-        }
-        cp_async_commit();
-    };
-
     stamp(P, 0);
-    int staged_chunk = -1, staged_kc0 = -1;
-    if (whiten && (int)blockIdx.x < P.n_chunks) {
-        stage_W(blockIdx.x, 0);            // lands while phase A streams the map
-        staged_chunk = blockIdx.x;
-        staged_kc0 = 0;
-    }
+    int conv_unit = -1;                      // which projection unit's W tile currently sits in Bt
+    const bool own_unit = whiten && (int)blockIdx.x < P.units;
 
     // ------------------------------------------------------------------ phase A
     {
@@ -259,7 +322,15 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
                 const int c = (int)(held_row % P.C);
                 const long long n = held_row / P.C;
                 const float pl = gem ? __ldg(P.p + c * P.p_stride) : 1.0f;
-                P.pooled[n * P.pooled_ld + c] = finish_row(classify_p(P.pool_mode, pl), held, HW, pl);
+                const float v = finish_row(classify_p(P.pool_mode, pl), held, HW, pl);
+                if (P.pooled_hi) {
+                    // the projection consumes bf16 hi + lo operands: split once here instead of in all 148 CTAs
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    P.pooled_hi[n * P.C + c] = h;
+                    P.pooled_lo[n * P.C + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+                } else {
+                    P.pooled[n * P.pooled_ld + c] = v;
+                }
             }
             held_row = -1;
         };
@@ -271,10 +342,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
         if (P.bulk_ok) {
             const int rps = max(1, TAIL_SLOT_BYTES / (HW * 4));            // rows per slot
             const int iters = (my_rows + rps - 1) / rps;
+            // gap between two rows of a consumer warp: at most TAIL_CONSUMERS iterations (+1)
+            const int nbar = min(TAIL_MAX_BARS, P.n_slots * ((TAIL_CONSUMERS + 1 + P.n_slots - 1) / P.n_slots + 1));
             if (tid == 0) {
-                for (int s = 0; s < P.n_slots; ++s) {
+                for (int s = 0; s < nbar; ++s) {
                     mbar_init(&full_bar[s], 1);
-                    mbar_init(&empty_bar[s], TAIL_CONSUMERS);
+                    mbar_init(&empty_bar[s], rps);       // one arrival per consumed row (a short last slot is never refilled)
                 }
                 fence_barrier_init();
             }
@@ -282,41 +355,62 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
             if (warp == TAIL_CONSUMERS) {
                 if (lane == 0) {
                     const uint64_t pol = policy_evict_first();
-                    int slot = 0;
-                    uint32_t phase = 0;
+                    int slot = 0, bar = 0, ebar = 0;          // data slot, barrier of iteration t, barrier of iteration t - n_slots
+                    uint32_t epar = 0;
                     for (int t = 0; t < iters; ++t) {
-                        mbar_wait(&empty_bar[slot], phase ^ 1u);
+                        if (t >= P.n_slots) {                  // the slot's previous rows (iteration t - n_slots) are consumed
+                            mbar_wait(&empty_bar[ebar], epar);
+                            if (++ebar == nbar) { ebar = 0; epar ^= 1u; }
+                        }
                         const int nr = min(rps, my_rows - t * rps);
                         const uint32_t bytes = (uint32_t)nr * (uint32_t)HW * 4u;
-                        mbar_arrive_expect_tx(&full_bar[slot], bytes);
+                        mbar_arrive_expect_tx(&full_bar[bar], bytes);
                         bulk_load(ring + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
-                                  &full_bar[slot], pol);
-                        if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
+                                  &full_bar[bar], pol);
+                        if (++slot == P.n_slots) slot = 0;
+                        if (++bar == nbar) bar = 0;
                     }
                 }
             } else {
-                int slot = 0;
-                uint32_t phase = 0;
-                // the exponent class is warp-uniform per row; with a shared p it is constant
-                for (int t = 0; t < iters; ++t) {
-                    mbar_wait(&full_bar[slot], phase);
-                    const int nr = min(rps, my_rows - t * rps);
-                    const int base = t * rps;
-                    int j = (warp - base % TAIL_CONSUMERS + TAIL_CONSUMERS) % TAIL_CONSUMERS;   // first local row with (base + j) % 15 == warp
-                    for (; j < nr; j += TAIL_CONSUMERS) {
-                        const long long row = r0 + base + j;
+                // consumer warps; the consumer count is a compile-time constant in either variant (no runtime modulo)
+                auto consume = [&](auto nc_tag) {
+                    constexpr int NC = decltype(nc_tag)::value;
+                    // this CTA's W tile -> bf16 hi / lo UMMA tiles, spread over the 480 consumer lanes in three
+                    // batches of 4 chunks interleaved with the row stream (each batch: 8 loads in flight per lane)
+                    constexpr int CONV_BATCHES = (TAIL_W_TASKS + NC * 32 * 4 - 1) / (NC * 32 * 4);
+                    const int my_count = (my_rows - warp + NC - 1) / NC;            // rows this warp will take
+                    const int conv_every = max(1, my_count / (CONV_BATCHES + 1));
+                    int conv_done = 0, taken = 0;
+                    // warp w takes local rows w, w + NC, ...; it only touches the barriers of the slots holding them
+                    int j = warp, slot = 0, bar = 0;
+                    uint32_t par = 0;
+                    for (int i = warp; i < my_rows; i += NC, j += NC) {
+                        while (j >= rps) {                      // advance to the slot iteration holding row i
+                            j -= rps;
+                            if (++slot == P.n_slots) slot = 0;
+                            if (++bar == nbar) { bar = 0; par ^= 1u; }
+                        }
+                        mbar_wait(&full_bar[bar], par);
+                        const long long row = r0 + i;
                         const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
                         const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
                         const float a = row_reduce<false>(classify_p(P.pool_mode, pr), src, HW, true, lane, P.eps_gem, pr);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
                         take(a, row);
+                        if (own_unit && conv_done < CONV_BATCHES && ++taken == (conv_done + 1) * conv_every) {
+                            convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, 1);
+                            ++conv_done;
+                        }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[slot]);
-                    if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
-                }
-                flush();
+                    if (own_unit && conv_done < CONV_BATCHES)      // short streams: whatever is left
+                        convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, CONV_BATCHES - conv_done);
+                    flush();
+                };
+                consume(std::integral_constant<int, TAIL_CONSUMERS>{});
             }
         } else {
+            if (own_unit) convert_w_tile<2>(P, Bt, blockIdx.x, tid, TAIL_THREADS);
             // direct loads: every warp takes rows r0 + warp, r0 + warp + 16, ...
             for (int j = warp; j < my_rows; j += TAIL_WARPS) {
                 const long long row = r0 + j;
@@ -326,6 +420,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
             }
             flush();
         }
+        if (own_unit) conv_unit = blockIdx.x;
     }
     stamp(P, 1);
     if (pool_only) return;
@@ -354,220 +449,188 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_fused_kernel(const TailP
         return;
     }
 
-    // ------------------------------------------------------------------ phase B
-    {
-        float* red_acc = red;                               // [8 wk][8 combo][32 lanes][4]
-        float* red_ss = red_acc + 8 * 8 * 32 * 4;           // [8 wk][64]
-        float* ysq = red_ss + 8 * TAIL_MB;                  // [64][16]
-        float* inv_s = ysq + TAIL_MB * TAIL_JMAX;           // [64]
-        const int g = lane >> 2, tig = lane & 3;
-        const int wm = warp & 1, wk = warp >> 1;            // image half, K range
-        for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-            const int j0 = chunk * P.jch;
-            const int J = min(P.jch, P.D_out - j0);
+    // ------------------------------------------------------------------ phase B: split-K projection units
+    if ((int)blockIdx.x < P.units) {
+        constexpr uint32_t idesc = make_idesc_bf16(TAIL_MB, TAIL_NT);
+        if (tid == 0) {
+            for (int s2 = 0; s2 < P.n_slots; ++s2) {
+                mbar_init(&fullB[s2], 1);
+                mbar_init(&emptyB[s2], 1);          // freed by tcgen05.commit
+            }
+            mbar_init(&accB, 1);
+            fence_barrier_init();
+            prefetch_tmap(&tmHi);
+            prefetch_tmap(&tmLo);
+        }
+        if (warp == 2) {
+            tmem_alloc(&tmem_slot, TAIL_NT);
+            tmem_relinquish();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_slot;
+        int slot = 0;               // ring position of the producer / the MMA issuer (same tile sequence)
+        uint32_t phase = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
+            const int nt = unit % P.n_ntiles, ks = unit / P.n_ntiles;
+            if (conv_unit != unit) {
+                // (more units than CTAs) the previous unit's MMAs have retired: its epilogue waited for them
+                __syncthreads();
+                convert_w_tile<2>(P, Bt, unit, tid, TAIL_THREADS);
+                conv_unit = unit;
+                __syncthreads();
+            }
+            const int kw = min(TAIL_KS, P.C - ks * TAIL_KS);
+            const int nkb = (kw + 63) >> 6;
             for (int n0 = 0; n0 < P.N; n0 += TAIL_MB) {
-                float acc[2][2][4];
-                float ss[2][2];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int x2 = 0; x2 < 2; ++x2) {
-                        ss[mt][x2] = 0.0f;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[mt][x2][r] = 0.0f;
-                    }
-                for (int kc0 = 0; kc0 < P.C; kc0 += TAIL_KC) {
-                    if (staged_chunk != chunk || staged_kc0 != kc0) {
-                        __syncthreads();      // everyone is done with the previous tile
-                        stage_W(chunk, kc0);
-                        staged_chunk = chunk;
-                        staged_kc0 = kc0;
-                    }
-                    cp_async_wait_all();
-                    __syncthreads();
-                    const int kw = min(TAIL_KC, P.C - kc0);
-                    // this warp's K range inside the tile, in blocks of 32
-                    const int kr0 = wk * (TAIL_KC / 8);
-                    const int nblk = max(0, min(TAIL_KC / 8, kw - kr0) + 31) >> 5;
-                    // rows (images) of the 4 fragment row slots: [mt][rsel]
-                    const float* arow[2][2];
-                    bool aok[2][2];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                        for (int rs = 0; rs < 2; ++rs) {
-                            const int n = n0 + wm * 32 + mt * 16 + g + rs * 8;
-                            aok[mt][rs] = n < P.N;
-                            arow[mt][rs] = P.pooled + (size_t)(aok[mt][rs] ? n : 0) * P.pooled_ld + kc0 + kr0 + tig * 8;
-                        }
-                    auto load_a = [&](int blk, float4 (&a)[2][2][2]) {
-                        const int kk = kr0 + blk * 32 + tig * 8;
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                            for (int rs = 0; rs < 2; ++rs)
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    a[mt][rs][h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (aok[mt][rs] && kk + h * 4 < kw)
-                                        a[mt][rs][h] = __ldcg(reinterpret_cast<const float4*>(arow[mt][rs] + blk * 32 + h * 4));
-                                }
-                    };
-                    // CTAs start at different blocks so that they do not hit the same L2 lines at the same moment
-                    int blk = nblk > 0 ? (int)(blockIdx.x % (unsigned)nblk) : 0;
-                    float4 a_next[2][2][2];
-                    if (nblk > 0) load_a(blk, a_next);
-                    for (int t = 0; t < nblk; ++t) {
-                        float4 a[2][2][2];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                            for (int rs = 0; rs < 2; ++rs)
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) a[mt][rs][h] = a_next[mt][rs][h];
-                        const int kk = kr0 + blk * 32 + tig * 8;
-                        if (++blk == nblk) blk = 0;
-                        if (t + 1 < nblk) load_a(blk, a_next);
-                        // B fragments of the two 8-dim tiles: W rows j = nt*8 + g, the same 8 consecutive k as A
-                        uint32_t bhi[2][2][2], blo[2][2][2];     // [nt][kstep][reg]
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt) {
-                            const int j = nt * 8 + g;
-                            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-                            if (j < J && kk < kw) w0 = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + kk]);
-                            if (j < J && kk + 4 < kw) w1 = *reinterpret_cast<const float4*>(&Ws[j * TAIL_KC + kk + 4]);
-                            split2(w0.x, w0.y, bhi[nt][0][0], blo[nt][0][0]);
-                            split2(w0.z, w0.w, bhi[nt][0][1], blo[nt][0][1]);
-                            split2(w1.x, w1.y, bhi[nt][1][0], blo[nt][1][0]);
-                            split2(w1.z, w1.w, bhi[nt][1][1], blo[nt][1][1]);
-                        }
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-                            for (int rs = 0; rs < 2; ++rs) {
-                                const float4 u = a[mt][rs][0], v = a[mt][rs][1];
-                                ss[mt][rs] += (u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w) + (v.x * v.x + v.y * v.y) +
-                                              (v.z * v.z + v.w * v.w);
-                            }
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                // k step ks uses the floats 4*ks .. 4*ks+3 of the lane's 8: slots (2 tig, 2 tig + 1) and (+8, +9)
-                                const float4 r0v = a[mt][0][ks], r1v = a[mt][1][ks];
-                                uint32_t ahi[4], alo[4];
-                                split2(r0v.x, r0v.y, ahi[0], alo[0]);
-                                split2(r1v.x, r1v.y, ahi[1], alo[1]);
-                                split2(r0v.z, r0v.w, ahi[2], alo[2]);
-                                split2(r1v.z, r1v.w, ahi[3], alo[3]);
-#pragma unroll
-                                for (int nt = 0; nt < 2; ++nt) {
-                                    mma_bf16_16816(acc[mt][nt], ahi, bhi[nt][ks]);
-                                    mma_bf16_16816(acc[mt][nt], ahi, blo[nt][ks]);
-                                    mma_bf16_16816(acc[mt][nt], alo, bhi[nt][ks]);
-                                }
+                if (warp == 0) {
+                    if (lane == 0) {
+                        for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll 1
+                            for (int part = 0; part < 2; ++part) {
+                                mbar_wait(&emptyB[slot], phase ^ 1u);
+                                mbar_arrive_expect_tx(&fullB[slot], TAIL_SLOT_BYTES);
+                                tma_load_2d(ring + (size_t)slot * TAIL_SLOT_BYTES, part ? &tmLo : &tmHi, &fullB[slot],
+                                            ks * TAIL_KS + kb * 64, n0);
+                                if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
                             }
                         }
                     }
-                }
-                // ---- reduce the 8 K ranges through shared memory
-                __syncthreads();   // the ring / previous pass scratch is free
+                } else if (warp == 1) {
+                    if (lane == 0) {
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            const int s_hi = slot;
+                            const uint32_t ph_hi = phase;
+                            if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
+                            const int s_lo = slot;
+                            const uint32_t ph_lo = phase;
+                            if (++slot == P.n_slots) { slot = 0; phase ^= 1u; }
+                            mbar_wait(&fullB[s_hi], ph_hi);
+                            mbar_wait(&fullB[s_lo], ph_lo);
+                            tc_fence_after();
+                            const uint64_t a_hi = make_sw128_desc(smem_u32(ring + (size_t)s_hi * TAIL_SLOT_BYTES));
+                            const uint64_t a_lo = make_sw128_desc(smem_u32(ring + (size_t)s_lo * TAIL_SLOT_BYTES));
+                            const uint64_t b_hi = make_sw128_desc(smem_u32(Bt + (size_t)(kb * 2) * TAIL_BT_BYTES));
+                            const uint64_t b_lo = make_sw128_desc(smem_u32(Bt + (size_t)(kb * 2 + 1) * TAIL_BT_BYTES));
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const int combo = (wm * 2 + mt) * 2 + nt;
-                        *reinterpret_cast<float4*>(&red_acc[((wk * 8 + combo) * 32 + lane) * 4]) =
-                            make_float4(acc[mt][nt][0], acc[mt][nt][1], acc[mt][nt][2], acc[mt][nt][3]);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t o = (uint64_t)(kk * 2);
+                                umma_bf16(tmem_acc, a_hi + o, b_hi + o, idesc, (uint32_t)((kb | kk) != 0));
+                                umma_bf16(tmem_acc, a_hi + o, b_lo + o, idesc, 1u);
+                                umma_bf16(tmem_acc, a_lo + o, b_hi + o, idesc, 1u);
+                            }
+                            umma_commit(&emptyB[s_hi]);
+                            umma_commit(&emptyB[s_lo]);
+                        }
+                        umma_commit(&accB);           // accumulator of this (unit, image block) complete
                     }
+                } else if (warp >= 8 && warp < 12) {
+                    // epilogue: TMEM -> this K slice's partial projection (fp32, stays in L2 for phase C)
+                    mbar_wait(&accB, acc_phase);
+                    tc_fence_after();
+                    const int quad = warp & 3;
+                    const int n = n0 + quad * 32 + lane;
+                    float* dst = P.part + ((size_t)ks * P.N + (size_t)(n < P.N ? n : 0)) * P.D_out + nt * TAIL_NT;
+#pragma unroll 1
+                    for (int cchunk = 0; cchunk < TAIL_NT / 32; ++cchunk) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cchunk * 32), v);
+                        tmem_ld_wait();
+                        if (n < P.N) {
+                            const int d0 = nt * TAIL_NT + cchunk * 32;
+                            if (d0 + 32 <= P.D_out && (P.D_out & 3) == 0) {
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                                for (int j = 0; j < 32; j += 4)
+                                    __stcg(reinterpret_cast<float4*>(dst + cchunk * 32 + j),
+                                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                       __uint_as_float(v[j + 3])));
+                            } else {
 #pragma unroll
-                    for (int rs = 0; rs < 2; ++rs) {
-                        float s = ss[mt][rs];
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        s += __shfl_xor_sync(0xffffffffu, s, 2);
-                        if (tig == 0) red_ss[wk * TAIL_MB + wm * 32 + mt * 16 + g + rs * 8] = s;
+                                for (int j = 0; j < 32; ++j)
+                                    if (d0 + j < P.D_out) dst[cchunk * 32 + j] = __uint_as_float(v[j]);
+                            }
+                        }
                     }
-                __syncthreads();
-                if (tid < TAIL_MB) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) s += red_ss[k8 * TAIL_MB + tid];
-                    inv_s[tid] = 1.0f / (sqrtf(s) + P.eps_l2);      // first L2N: W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
+                    tc_fence_before();
                 }
-                __syncthreads();
-                {
-                    // thread (warp, lane): tile combo = warp & 7, fragment row half = warp >> 3
-                    const int combo = warp & 7, rp = warp >> 3;
-                    const int cwm = combo >> 2, cmt = (combo >> 1) & 1, cnt = combo & 1;
-                    float y0 = 0.0f, y1 = 0.0f;
-#pragma unroll
-                    for (int k8 = 0; k8 < 8; ++k8) {
-                        const float2 v = *reinterpret_cast<const float2*>(&red_acc[((k8 * 8 + combo) * 32 + lane) * 4 + rp * 2]);
-                        y0 += v.x;
-                        y1 += v.y;
-                    }
-                    const int nl = cwm * 32 + cmt * 16 + g + rp * 8;
-                    const int jl = cnt * 8 + tig * 2;
-                    const int n = n0 + nl;
-                    const float inv = inv_s[nl];
-                    y0 = y0 * inv + ((jl < J && P.bias) ? __ldg(P.bias + j0 + jl) : 0.0f);
-                    y1 = y1 * inv + ((jl + 1 < J && P.bias) ? __ldg(P.bias + j0 + jl + 1) : 0.0f);
-                    if (jl >= J) y0 = 0.0f;
-                    if (jl + 1 >= J) y1 = 0.0f;
-                    if (n < P.N) {
-                        if (jl < J) P.out[(size_t)n * P.out_ld + j0 + jl] = y0;
-                        if (jl + 1 < J) P.out[(size_t)n * P.out_ld + j0 + jl + 1] = y1;
-                    }
-                    ysq[nl * TAIL_JMAX + jl] = y0 * y0;
-                    ysq[nl * TAIL_JMAX + jl + 1] = y1 * y1;
-                }
-                __syncthreads();
-                if (tid < TAIL_MB && n0 + tid < P.N) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < TAIL_JMAX; ++j) s += ysq[tid * TAIL_JMAX + j];
-                    P.partial[(size_t)chunk * P.N + n0 + tid] = s;
-                }
+                acc_phase ^= 1u;
+                __syncthreads();          // TMEM is free for the next image block / unit
             }
         }
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_acc, TAIL_NT);
     }
 
     stamp(P, 3);
     grid.sync();
     stamp(P, 4);
 
-    // ------------------------------------------------------------------ phase C: second L2N
-    // per image: sum the chunks' partial sums of squares in a fixed order (deterministic), then rescale
-    // the J columns this CTA wrote.
+    // ------------------------------------------------------------------ phase C: one CTA per image
     {
-        constexpr int CB = 64;                       // images per pass
-        constexpr int PARTS = TAIL_THREADS / CB;     // 8 chunk subsets
-        __shared__ float redc[PARTS][CB];
-        __shared__ float denom_s[CB];
-        for (int chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-            const int j0 = chunk * P.jch;
-            const int J = min(P.jch, P.D_out - j0);
-            for (int n0 = 0; n0 < P.N; n0 += CB) {
-                const int nl = tid & (CB - 1), part = tid / CB;
-                float sacc = 0.0f;
-                if (n0 + nl < P.N)
-                    for (int ch = part; ch < P.n_chunks; ch += PARTS) sacc += __ldcg(P.partial + (size_t)ch * P.N + n0 + nl);
-                redc[part][nl] = sacc;
-                __syncthreads();
-                if (tid < CB) {
-                    float tot = 0.0f;
+        __shared__ float redc[TAIL_WARPS];
+        __shared__ float bcast;
+        auto block_sum = [&](float v) -> float {       // deterministic: fixed shuffle tree, then warps in order
+            v = warp_sum(v);
+            __syncthreads();
+            if (lane == 0) redc[warp] = v;
+            __syncthreads();
+            if (tid == 0) {
+                float t = 0.0f;
 #pragma unroll
-                    for (int pp = 0; pp < PARTS; ++pp) tot += redc[pp][tid];
-                    denom_s[tid] = sqrtf(tot) + P.eps_l2;
+                for (int w = 0; w < TAIL_WARPS; ++w) t += redc[w];
+                bcast = t;
+            }
+            __syncthreads();
+            return bcast;
+        };
+        for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+            // issue everything that does not depend on a reduction first: the K-slice partial sums (fixed order)
+            constexpr int YR = 8;
+            float yreg[YR];
+            const bool in_regs = P.D_out <= YR * TAIL_THREADS;
+#pragma unroll
+            for (int i = 0; i < YR; ++i) {
+                const int d = tid + i * TAIL_THREADS;
+                yreg[i] = 0.0f;
+                if (d < P.D_out)
+                    for (int ks = 0; ks < P.n_kslices; ++ks) yreg[i] += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
+            }
+            // first L2N: ||g_n|| from the split pooled vector
+            float sg = 0.0f;
+            for (int c = tid * 8; c < P.C; c += TAIL_THREADS * 8)
+                sg += sumsq8(__ldcg(reinterpret_cast<const uint4*>(P.pooled_hi + (size_t)n * P.C + c)),
+                             __ldcg(reinterpret_cast<const uint4*>(P.pooled_lo + (size_t)n * P.C + c)));
+            const float inv = 1.0f / (sqrtf(block_sum(sg)) + P.eps_l2);     // W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
+            float sy = 0.0f;
+#pragma unroll
+            for (int i = 0; i < YR; ++i) {
+                const int d = tid + i * TAIL_THREADS;
+                if (d < P.D_out) {
+                    yreg[i] = yreg[i] * inv + (P.bias ? __ldg(P.bias + d) : 0.0f);
+                    sy = fmaf(yreg[i], yreg[i], sy);
                 }
-                __syncthreads();
-                const int cnt = min(CB, P.N - n0) * J;
-                for (int e = tid; e < cnt; e += TAIL_THREADS) {
-                    const int n = e / J, j = e - n * J;
-                    float* o = P.out + (size_t)(n0 + n) * P.out_ld + j0 + j;
-                    *o = __ldcg(o) / denom_s[n];
+            }
+            for (int d = tid + YR * TAIL_THREADS; d < P.D_out; d += TAIL_THREADS) {
+                float acc = 0.0f;
+                for (int ks = 0; ks < P.n_kslices; ++ks) acc += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
+                const float y = acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f);
+                sy = fmaf(y, y, sy);
+            }
+            const float denom = sqrtf(block_sum(sy)) + P.eps_l2;
+#pragma unroll
+            for (int i = 0; i < YR; ++i) {
+                const int d = tid + i * TAIL_THREADS;
+                if (d < P.D_out) P.out[(size_t)n * P.out_ld + d] = yreg[i] / denom;
+            }
+            if (!in_regs) {
+                for (int d = tid + YR * TAIL_THREADS; d < P.D_out; d += TAIL_THREADS) {
+                    float acc = 0.0f;
+                    for (int ks = 0; ks < P.n_kslices; ++ks) acc += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
+                    P.out[(size_t)n * P.out_ld + d] = (acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f)) / denom;
                 }
-                __syncthreads();
             }
         }
     }
@@ -597,8 +660,9 @@ using namespace cir;
 
 extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) {
     CIR_REQUIRE(bytes && N > 0 && C > 0 && D_out > 0, CIR_ERR_INVALID_ARG, "cir_tail_workspace_bytes: bad arguments");
-    // pooled [N, C] + partial [D_out, N] (n_chunks <= D_out) + debug stamps
-    *bytes = align_up((size_t)N * C * 4, 256) + align_up((size_t)D_out * N * 4, 256) + TAIL_STAMP_BYTES;
+    // pooled [N, C] (fp32, or bf16 hi + lo) + part [ceil(C / 256)][N][D_out] + debug stamps
+    const size_t kslices = ((size_t)C + TAIL_KS - 1) / TAIL_KS;
+    *bytes = align_up((size_t)N * C * 4, 256) + align_up(kslices * (size_t)N * D_out * 4, 256) + TAIL_STAMP_BYTES;
     return CIR_OK;
 }
 
@@ -638,38 +702,47 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
                     "cir_tail_fwd: workspace must be 16 B aligned");
         P.pooled = static_cast<float*>(workspace);
         P.pooled_ld = C;
-        P.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)N * C * 4, 256));
+        P.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up((size_t)N * C * 4, 256));
         if (flags & CIR_TAIL_DEBUG_STAMPS)
             P.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + need - TAIL_STAMP_BYTES);
     }
     if (whiten) {
         CIR_REQUIRE(Wt, CIR_ERR_INVALID_ARG, "cir_tail_fwd: whitening needs Wt");
-        CIR_REQUIRE((C & 3) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0, CIR_ERR_UNSUPPORTED,
-                    "cir_tail_fwd: whitening needs C %% 4 == 0 and a 16 B aligned Wt (C=%d)", C);
-        int jch = (D_out + grid - 1) / grid;
-        if (jch > TAIL_JMAX) jch = TAIL_JMAX;
-        P.jch = jch;
-        P.n_chunks = (D_out + jch - 1) / jch;
-        P.w_bytes = (int)align_up((size_t)jch * TAIL_KC * sizeof(float), 1024);
+        CIR_REQUIRE((C & 7) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0, CIR_ERR_UNSUPPORTED,
+                    "cir_tail_fwd: whitening needs C %% 8 == 0 and a 16 B aligned Wt (C=%d)", C);
+        P.pooled_hi = reinterpret_cast<__nv_bfloat16*>(P.pooled);
+        P.pooled_lo = P.pooled_hi + (size_t)N * C;
+        P.n_ntiles = (D_out + TAIL_NT - 1) / TAIL_NT;
+        P.n_kslices = (C + TAIL_KS - 1) / TAIL_KS;
+        P.units = P.n_ntiles * P.n_kslices;
+        P.w_bytes = TAIL_W_BYTES;
     }
     // ring: as many 16 KB slots as fit beside the W slice (and at least the phase-B scratch)
-    const int static_smem = 4096;     // barriers + phase-C arrays, with slack
-    int slots = (dev.max_smem_optin - static_smem - P.w_bytes) / TAIL_SLOT_BYTES;
+    const int static_smem = 2048;     // barriers + reduction scratch (1.5 KB today), with slack
+    int slots = (dev.max_smem_optin - static_smem - 1024 - P.w_bytes) / TAIL_SLOT_BYTES;
     if (slots > TAIL_MAX_SLOTS) slots = TAIL_MAX_SLOTS;
-    const int min_slots = (int)((TAIL_RED_FLOATS * sizeof(float) + TAIL_SLOT_BYTES - 1) / TAIL_SLOT_BYTES);
-    CIR_REQUIRE(slots >= (whiten ? min_slots : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
+    CIR_REQUIRE(slots >= (whiten ? 2 : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
     P.n_slots = slots;
-    const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES;
+    const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES + 1024 /* 1 KB alignment of the tiles */;
+    CUtensorMap tmHi, tmLo;
+    memset(&tmHi, 0, sizeof(tmHi));
+    memset(&tmLo, 0, sizeof(tmLo));
+    if (whiten) {
+        int rc = make_tmap_bf16(&tmHi, P.pooled_hi, (uint64_t)N, (uint64_t)C, (uint64_t)C, TAIL_MB);
+        if (rc) return rc;
+        rc = make_tmap_bf16(&tmLo, P.pooled_lo, (uint64_t)N, (uint64_t)C, (uint64_t)C, TAIL_MB);
+        if (rc) return rc;
+    }
     static thread_local int attr_set_dev = -1;
     if (attr_set_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             dev.max_smem_optin - static_smem));
         attr_set_dev = dev.device;
     }
-    void* args[] = {&P};
+    void* args[] = {&tmHi, &tmLo, &P};
     if (pool_only) {
         // no grid barrier on this path: a plain launch is enough
-        tail_fused_kernel<<<grid, TAIL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(P);
+        tail_fused_kernel<<<grid, TAIL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmHi, tmLo, P);
         CIR_CHECK_CUDA(cudaGetLastError());
     } else {
         CIR_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)tail_fused_kernel, dim3(grid), dim3(TAIL_THREADS),
