@@ -31,6 +31,7 @@ SIGNATURES = {
                               _vp, _vp, _c_int, _vp, _c_int, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_gem_bwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp]),
     "cir_bias_l2n_rows": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _vp, _c_f, _vp, _c_i64, _vp]),
+    "cir_powerlaw": (_c_int, [_vp, _c_i64, _c_f, _vp, _vp]),
     "cir_l2n_rows": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _c_f, _vp, _c_i64, _vp]),
     "cir_pack_bf16": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp]),
     "cir_search_workspace_bytes": (_c_int, [_c_int, _c_i64, _c_int, _c_int, _szp]),

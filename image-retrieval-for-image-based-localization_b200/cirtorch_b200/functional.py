@@ -274,3 +274,14 @@ def l2n(x, eps=1e-6):
     if moved is None:
         return y.reshape(shape)
     return y.reshape(moved.shape).movedim(-1, 1)
+
+
+def powerlaw(x, eps=1e-6):
+    """sign(x + eps) * sqrt(|x + eps|), cirtorch/modules/normalizations.py:25-27 (inference only)."""
+    _lib.require_cuda(x)
+    lib = _lib.load()
+    xc = _as_f32_contig(x)
+    out = torch.empty_like(xc)
+    rc = lib.cir_powerlaw(_lib.ptr(xc), xc.numel(), float(eps), _lib.ptr(out), _lib.stream_of(xc))
+    _lib.check(rc, "cir_powerlaw")
+    return out

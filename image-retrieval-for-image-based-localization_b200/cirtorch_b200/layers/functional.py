@@ -1,1 +1,1 @@
-from ..functional import gem, mac, spoc, l2n, descriptor_tail  # noqa: F401
+from ..functional import gem, mac, spoc, l2n, powerlaw, descriptor_tail  # noqa: F401

@@ -1,1 +1,1 @@
-from ..modules.normalizations import L2N, NORMALIZATION_LAYERS  # noqa: F401
+from ..modules.normalizations import L2N, PowerLaw, NORMALIZATION_LAYERS  # noqa: F401

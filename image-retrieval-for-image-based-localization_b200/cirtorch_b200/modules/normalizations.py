@@ -18,6 +18,21 @@ class L2N(nn.Module):
         return self.__class__.__name__ + "(eps=%s)" % self.eps
 
 
+class PowerLaw(nn.Module):
+    """Signed square root (normalizations.py:19-27)."""
+
+    def __init__(self, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x):
+        return LF.powerlaw(x, eps=self.eps)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "(eps=%s)" % self.eps
+
+
 NORMALIZATION_LAYERS = {
     "L2N": L2N,
+    "PowerLaw": PowerLaw,
 }

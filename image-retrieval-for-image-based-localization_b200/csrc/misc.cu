@@ -154,9 +154,31 @@ mine_filter_kernel(const int32_t* __restrict__ cand, int Q, int Kc, const int32_
     }
 }
 
+// ------------------------------------------------------------------------------ PowerLaw
+// cirtorch/modules/normalizations.py:19-27:  y = sign(x + eps) * sqrt(|x + eps|)
+__global__ void __launch_bounds__(256)
+powerlaw_kernel(const float* __restrict__ x, long long n, float eps, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i] + eps;
+    out[i] = copysignf(sqrtf(fabsf(v)), v) * (v == 0.0f ? 0.0f : 1.0f);
+}
+
 }  // namespace cir
 
 using namespace cir;
+
+extern "C" int cir_powerlaw(const float* x, int64_t n, float eps, float* out, void* stream) {
+    CIR_REQUIRE(x && out && n >= 0, CIR_ERR_INVALID_ARG, "cir_powerlaw: bad arguments");
+    if (n == 0) return CIR_OK;
+    const long long blocks = (n + 255) / 256;
+    CIR_REQUIRE(blocks <= 0x7fffffffll, CIR_ERR_UNSUPPORTED, "cir_powerlaw: too many elements");
+    powerlaw_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, eps, out);
+    CIR_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CIR_OK;
+}
+
 
 extern "C" int cir_pack_bf16(const float* src, int64_t rows, int D, int64_t src_ld, void* dst, int64_t dst_ld, int n_split,
                              int role, void* stream) {

@@ -99,6 +99,9 @@ int cir_gem_bwd(const float* x, int N, int C, int H, int W, const float* p, int 
 int cir_bias_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, const float* bias,
                       float eps_l2, float* out, int64_t out_ld, void* stream);
 
+/* PowerLaw.forward (cirtorch/modules/normalizations.py:19-27): out = sign(x + eps) * sqrt(|x + eps|), elementwise */
+int cir_powerlaw(const float* x, int64_t n, float eps, float* out, void* stream);
+
 /* row-wise L2N in place or out of place: L2N.forward on [N, C] rows (normalizations.py:15) */
 int cir_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, float eps,
                  float* out, int64_t out_ld, void* stream);

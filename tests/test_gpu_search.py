@@ -245,3 +245,15 @@ def test_million_row_database_properties(Q):
         parts.append(sh.search_rows(q, k, rescore=False))
     ms, mi = S.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
     assert torch.equal(mi, i_g) and torch.equal(ms, s_g)
+
+
+def test_index_save_load_roundtrip(tmp_path):
+    from cirtorch_b200 import search as S, store
+    db, _ = clustered_unit_rows(3000, 128, 30, 0.6, seed=12)
+    q, _ = clustered_unit_rows(20, 128, 30, 0.6, seed=12)
+    index = S.Index(_dev(db), mode="bf16", row_offset=1000)
+    s0, i0 = index.search_rows(_dev(q), 10)
+    store.save_index(str(tmp_path / "shard.pt"), index, extra={"name": "shard0"})
+    index2 = store.load_index(str(tmp_path / "shard.pt"), device=DEV)
+    s1, i1 = index2.search_rows(_dev(q), 10)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1) and int(i1.min()) >= 1000

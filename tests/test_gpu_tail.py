@@ -110,6 +110,15 @@ def test_l2n_general_rank():
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-7)
 
 
+def test_powerlaw_matches_reference_formula():
+    from cirtorch_b200.modules.normalizations import NORMALIZATION_LAYERS
+    x = torch.randn(4, 33, 3, 5)
+    x[0, 0, 0, 0] = -1e-6                      # x + eps == 0
+    ref = (x + 1e-6).abs().sqrt().mul((x + 1e-6).sign())          # normalizations.py:25-27
+    out = NORMALIZATION_LAYERS["PowerLaw"]()(x.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-6, atol=1e-9)
+
+
 def test_gradients_match_autograd():
     """Training: p, W, b and x receive the gradients of the reference formula."""
     torch.manual_seed(3)

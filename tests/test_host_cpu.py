@@ -77,3 +77,31 @@ def test_shard_bounds_partition():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_store_formats_roundtrip(tmp_path):
+    """N3: dataset pickles with the reference's field names, snapshot ret_head loading (CPU only)."""
+    import pickle
+    import numpy as np
+    from cirtorch_b200 import store
+    from cirtorch_b200.modules.heads.global_head import globalHead
+    gnd = {"imlist": ["a", "b", "c"], "qimlist": ["q0"], "gnd": [{"bbx": [0, 0, 10, 10], "easy": [0], "hard": [1], "junk": [2]}]}
+    with open(tmp_path / "gnd_roxford5k.pkl", "wb") as f:
+        pickle.dump(gnd, f)
+    db = store.load_test_dataset(str(tmp_path), "roxford5k")
+    assert db["n_img"] == 3 and db["n_query"] == 1 and db["query_bbx"] == [[0, 0, 10, 10]]
+    assert db["img_names"][0].endswith("jpg/a.jpg") and db["dataset"] == "roxford5k"
+    with pytest.raises(ValueError):
+        store.load_test_dataset(str(tmp_path), "nope")
+    train = {"train": {"cids": ["x"] * 6, "cluster": [0, 0, 1, 1, 2, 2], "qidxs": [0, 2], "pidxs": [1, 3]}, "val": {}}
+    with open(tmp_path / "sfm.pkl", "wb") as f:
+        pickle.dump(train, f)
+    tdb = store.load_training_db(str(tmp_path / "sfm.pkl"), "train")
+    miner = store.miner_from_training_db(tdb, nnum=1, qsize=2, poolsize=6)
+    assert miner.qsize == 2 and miner.poolsize == 6 and list(miner.clusters) == [0, 0, 1, 1, 2, 2]
+    head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=8)
+    sd = {k: v.clone() + 1.0 for k, v in head.state_dict().items()}
+    sd["whiten.bias"] = torch.zeros(3)                     # wrong shape: skipped like _load_pretraining_dict
+    torch.save({"config": "", "state_dict": {"ret_head": sd, "body": {}}, "training_meta": {"epoch": 7}}, tmp_path / "snap.pth")
+    meta = store.load_ret_head(str(tmp_path / "snap.pth"), head)
+    assert meta["epoch"] == 7 and float(head.pool.p) == 4.0 and float(head.whiten.bias.abs().max()) == 0.0
