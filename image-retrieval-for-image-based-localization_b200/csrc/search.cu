@@ -27,6 +27,7 @@
 #include "search.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace cir {
 
@@ -42,7 +43,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SEARCH_THREADS = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-enum { MODE_TOPK = 0, MODE_DENSE = 1 };
+enum { MODE_TOPK = 0, MODE_DENSE = 1, MODE_GROUPMAX = 2 };
+constexpr int GROUP = 8;            // MODE_GROUPMAX: one value per 8 consecutive database rows
 
 struct SearchParams {
     int Q;
@@ -311,6 +313,22 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                 if (lane == l) { cnt = nc; tau = fmaxf(tau, nt_); }
                             }
                         }
+                    } else if (MODE == MODE_GROUPMAX) {
+                        // threshold pre-pass: only the maximum of every 8 consecutive rows leaves the SM (N % 256 == 0 here).
+                        // Each maximum is the score of a distinct row, so the k-th largest of them is a lower bound of the
+                        // query's k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.
+                        if (valid) {
+                            float m[32 / GROUP];
+#pragma unroll
+                            for (int g = 0; g < 32 / GROUP; ++g) {
+                                float x = __uint_as_float(v[g * GROUP]);
+#pragma unroll
+                                for (int j = 1; j < GROUP; ++j) x = fmaxf(x, __uint_as_float(v[g * GROUP + j]));
+                                m[g] = x;
+                            }
+                            *reinterpret_cast<float4*>(P.dense_out + (long long)qg * P.dense_ld + cb / GROUP) =
+                                make_float4(m[0], m[1], m[2], m[3]);
+                        }
                     } else {
                         if (valid) {
                             float* o = P.dense_out + (long long)qg * P.dense_ld + cb;
@@ -427,11 +445,14 @@ static int launch_search(int mode, const void* q, int Q, const void* db, long lo
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_dev = dev.device;
     }
     const int grid = plan.units < dev.num_sms ? plan.units : dev.num_sms;
     if (mode == MODE_TOPK)
         search_kernel<MODE_TOPK><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+    else if (mode == MODE_GROUPMAX)
+        search_kernel<MODE_GROUPMAX><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
     else
         search_kernel<MODE_DENSE><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
     CIR_CHECK_CUDA(cudaGetLastError());
@@ -453,16 +474,24 @@ static int check_operands(const char* who, const void* q, int Q, const void* db,
 
 using namespace cir;
 
-// Warm start of the running thresholds: the k-th best score of every query over the first n0 database
-// rows is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
+// Warm start of the running thresholds: the k-th best score of every query over (a subset of) the first n0
+// database rows is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
 // and most appends (measured 53.6 ms -> 30.9 ms on 10k x 1M with an exact tau0).
 static int sample_rows(int Q, long long N, int k) {
-    // ~N/32 rows (3 % extra scan), a power of two in [2048, 32768]; the dense sample block (Q * n0 * 4 bytes) is kept
-    // under 2 GiB; small databases skip the pre-pass.  10k x 1M: n0 = 32768 -> 33.8 ms, 16384 -> 34.7 ms, exact 32.5 ms.
+    // ~N/32 rows (3 % extra scan), a power of two in [2048, 32768]; small databases skip the pre-pass.
+    // 10k x 1M: n0 = 32768 -> 33.8 ms, 16384 -> 34.7 ms, exact 32.5 ms.
     if (N < 65536) return 0;
+    static const char* dbg = getenv("CIR_DEBUG_SAMPLE_ROWS");        // experiments only
     int n0 = 2048;
-    while (n0 * 2 <= KTH_MAX_N && (long long)n0 * 2 * 32 <= N + N / 2 && (long long)Q * n0 * 2 * 4 <= (2ll << 30)) n0 *= 2;
-    if (k > n0 / 8) return 0;
+    if (dbg && atoi(dbg) >= 2048) {
+        n0 = atoi(dbg) / 256 * 256;
+        if (n0 >= N) n0 = 2048;
+    } else {
+        while (n0 * 2 <= SAMPLE_MAX_ROWS && (long long)n0 * 2 * 32 <= N + N / 2) n0 *= 2;
+    }
+    // the k-th largest of n0 / 8 group maxima must stay a tight bound: at least 4 k groups when the database allows
+    while (k > n0 / GROUP / 4 && n0 * 2 <= SAMPLE_MAX_ROWS && (long long)n0 * 2 * 4 <= N) n0 *= 2;
+    if (k > n0 / GROUP / 2) return 0;
     return n0;
 }
 
@@ -475,7 +504,7 @@ static SearchWs search_ws_layout(const SearchPlan& plan, int Q, int cap, int n0)
     w.counts = w.lists + align_up((size_t)plan.S * plan.Qpad * cap * 8, 256);
     w.tau = w.counts + align_up((size_t)plan.S * plan.Qpad * 4, 256);
     w.dense = w.tau + align_up((size_t)plan.Qpad * 4, 256);
-    w.total = w.dense + align_up((size_t)Q * n0 * 4, 256);
+    w.total = w.dense + align_up((size_t)Q * (n0 / GROUP) * 4, 256);
     return w;
 }
 
@@ -532,16 +561,16 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
     char* ws = static_cast<char*>(workspace);
     const int n0 = (tau0 || q_label || (flags & CIR_SEARCH_NO_PREPASS)) ? 0 : n0_ws;
     if (n0 > 0) {
-        // pre-pass: dense scores of the first n0 rows, then the k-th largest per query
+        // pre-pass: maxima of every 8 consecutive rows of the first n0 rows, then the k-th largest of them per query
         float* dense = reinterpret_cast<float*>(ws + w.dense);
         float* tau = reinterpret_cast<float*>(ws + w.tau);
         SearchParams D{};
         D.dense_out = dense;
-        D.dense_ld = n0;
-        rc = launch_search(MODE_DENSE, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
+        D.dense_ld = n0 / GROUP;
+        rc = launch_search(MODE_GROUPMAX, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
                            static_cast<cudaStream_t>(stream));
         if (rc) return rc;
-        rc = launch_row_kth_largest(dense, Q, n0, n0, k, tau, static_cast<cudaStream_t>(stream));
+        rc = launch_row_kth_largest(dense, Q, n0 / GROUP, n0 / GROUP, k, tau, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
         tau0 = tau;
     }

@@ -26,5 +26,6 @@ int launch_topk_select_lists(const unsigned long long* lists, const int* counts,
 // tau0[q] = k-th largest of scores[q, 0:n) (n * 4 + 32 KB of shared memory per block)
 int launch_row_kth_largest(const float* scores, int Q, int n, long long ld, int k, float* out, cudaStream_t stream);
 constexpr int KTH_MAX_N = 32768;
+constexpr int SAMPLE_MAX_ROWS = 32768;   // rows of the threshold pre-pass
 
 }  // namespace cir

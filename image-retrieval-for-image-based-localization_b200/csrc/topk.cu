@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "search.cuh"
 
+#include <stdlib.h>
+
 namespace cir {
 
 constexpr int SEL_MAX_PEERS = 16;
@@ -68,83 +70,178 @@ struct SelParams {
 constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_MAX_KOUT = 1024;    // largest k the select / merge kernel emits
-constexpr int SEL_SMEM_BYTES = SEL_N * 8 + SEL_MAX_KOUT * 8 + SEL_WARPS * 256 * 4 + (2 * SEL_MAX_LISTS + 1 + 4 + 3) * 4;
+constexpr int SEL_SMEM_BYTES = SEL_N * 8 + SEL_MAX_KOUT * 8 + SEL_WARPS * 256 * 4 + (2 * SEL_MAX_LISTS + 1 + 8 + 3) * 4;
 
 template <int SRC> __global__ void topk_select_kernel(const struct SelParams p);
 template <int SRC>
 static int launch_select(const struct SelParams& p, int Q, cudaStream_t stream);
 
-// Keep the k largest of buf[0, fill) (fill > k): MSB-first radix select of the k-th largest 64-bit key
-// (8 passes of 8 bits, per-warp histograms), then the survivors are moved to buf[0, k) (unordered).
-// Far cheaper than sorting: ~8 x (fill / 512) key reads per thread instead of ~78 x 4 compare-exchanges.
+// Bin search shared by the radix selects: lane l of ONE warp owns bins 255 - 8 l ... 248 - 8 l of a 256-bin histogram
+// (descending); finds the bin where the running count from the top reaches krem.  Returns (on every lane) the bin, the
+// number of keys in higher bins and the number of keys in the bin itself.
+__device__ __forceinline__ void warp_find_bin(const int* hist, int krem, int lane, int* bin_out, int* before_out, int* cnt_out) {
+    int c[8], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = hist[255 - 8 * lane - i]; tot += c[i]; }
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int before = inc - tot;                     // keys in higher bins than this lane's
+    const bool mine = before < krem && krem <= inc;
+    int bin = 0, run = before, cb = 0;
+    if (mine) {
+        bin = 255 - 8 * lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (run + c[i] >= krem) { bin = 255 - 8 * lane - i; cb = c[i]; break; }
+            run += c[i];
+        }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = who ? __ffs(who) - 1 : 0;          // who == 0 only if fewer than krem keys exist (callers exclude it)
+    *bin_out = __shfl_sync(0xffffffffu, bin, src);
+    *before_out = __shfl_sync(0xffffffffu, run, src);
+    *cnt_out = __shfl_sync(0xffffffffu, cb, src);
+}
+
+__device__ __forceinline__ unsigned long long warp_and64(unsigned long long v) {
+    const uint32_t lo = __reduce_and_sync(0xffffffffu, (uint32_t)v), hi = __reduce_and_sync(0xffffffffu, (uint32_t)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// Keep the k largest of buf[0, fill) (fill > k, keys distinct): MSB-first radix select of a threshold key T with exactly k
+// keys >= T, then the survivors are moved to buf[0, k) (unordered).  The bits all keys share are skipped (one AND / OR
+// pass: candidate scores sit in a narrow range, so the top ~10 bits are common) and the select stops as soon as the
+// boundary bin is taken whole -- typically 2 histogram passes instead of 8.
 __device__ __forceinline__ void block_keep_topk(unsigned long long* buf, int fill, int k, int* hist /*[SEL_WARPS][256]*/,
-                                                unsigned long long* stage /*[SEL_MAX_KOUT]*/, int* s_misc /*[4]*/, int tid) {
+                                                unsigned long long* stage /*[SEL_MAX_KOUT]*/, int* s_misc /*[8]*/, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
-    unsigned long long prefix = 0ull;
+    unsigned long long a = ~0ull, o = 0ull;
+    for (int t = tid; t < fill; t += SEL_THREADS) { const unsigned long long key = buf[t]; a &= key; o |= key; }
+    a = warp_and64(a); o = warp_or64(o);
+    unsigned long long* s_ao = reinterpret_cast<unsigned long long*>(hist);      // [2][SEL_WARPS], before hist is used
+    if (lane == 0) { s_ao[warp] = a; s_ao[SEL_WARPS + warp] = o; }
+    __syncthreads();
+    a = ~0ull; o = 0ull;
+#pragma unroll
+    for (int w = 0; w < SEL_WARPS; ++w) { a &= s_ao[w]; o |= s_ao[SEL_WARPS + w]; }
+    __syncthreads();
+    const unsigned long long diff = a ^ o;
+    int bits = diff ? 64 - __clzll((long long)diff) : 0;         // undecided low bits
+    unsigned long long prefix = bits >= 64 ? 0ull : (a >> bits) << bits;
     int krem = k;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
+    while (bits > 0) {
+        const int w = bits < 8 ? bits : 8;
+        const int shift = bits - w;
+        const unsigned long long himask = bits >= 64 ? 0ull : ~((1ull << bits) - 1ull);
         for (int t = tid; t < SEL_WARPS * 256; t += SEL_THREADS) hist[t] = 0;
         __syncthreads();
         for (int t = tid; t < fill; t += SEL_THREADS) {
             const unsigned long long key = buf[t];
-            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
-                atomicAdd(&hist[warp * 256 + (int)((key >> shift) & 255ull)], 1);
+            if ((key & himask) == prefix) atomicAdd(&hist[warp * 256 + (int)((key >> shift) & (unsigned long long)((1 << w) - 1))], 1);
         }
         __syncthreads();
         if (tid < 256) {
             int c = 0;
 #pragma unroll
-            for (int w = 0; w < SEL_WARPS; ++w) c += hist[w * 256 + tid];
+            for (int w2 = 0; w2 < SEL_WARPS; ++w2) c += hist[w2 * 256 + tid];
             hist[tid] = c;                     // row 0 = block histogram
         }
         __syncthreads();
         if (warp == 0) {
-            // lane l owns bins 255 - 8 l ... 248 - 8 l (descending); find the bin where the running count reaches krem
-            int c[8], tot = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c[i] = hist[255 - 8 * lane - i]; tot += c[i]; }
-            int inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const int before = inc - tot;                     // keys in higher bins than this lane's
-            const bool mine = before < krem && krem <= inc;
-            if (mine) {
-                int run = before, bin = 255 - 8 * lane;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (run + c[i] >= krem) { bin = 255 - 8 * lane - i; break; }
-                    run += c[i];
-                }
-                s_misc[0] = bin;
-                s_misc[1] = krem - run;
-            }
+            int bin, before, cb;
+            warp_find_bin(hist, krem, lane, &bin, &before, &cb);
+            if (lane == 0) { s_misc[0] = bin; s_misc[1] = krem - before; s_misc[3] = cb; }
         }
         __syncthreads();
         prefix |= (unsigned long long)s_misc[0] << shift;
         krem = s_misc[1];
+        const int cb = s_misc[3];
+        bits = shift;
+        __syncthreads();
+        if (cb == krem) break;                  // the whole boundary bin is needed: every key >= prefix survives
     }
-    // prefix == the k-th largest key.  Survivors: everything greater, then equals until k are kept.
+    // survivors: everything above the boundary bin, then keys of the boundary bin until k are kept (the whole bin after an
+    // early exit; with duplicated keys -- empty slots -- whichever come first)
+    const unsigned long long thi = prefix | (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull));
     if (tid == 0) { s_misc[2] = 0; }
     __syncthreads();
     for (int t = tid; t < fill; t += SEL_THREADS) {
         const unsigned long long key = buf[t];
-        if (key > prefix) stage[atomicAdd(&s_misc[2], 1)] = key;
+        if (key > thi) stage[atomicAdd(&s_misc[2], 1)] = key;
     }
     __syncthreads();
     for (int t = tid; t < fill; t += SEL_THREADS) {
         const unsigned long long key = buf[t];
-        if (key == prefix) {
+        if (key >= prefix && key <= thi) {
             const int pos = atomicAdd(&s_misc[2], 1);
             if (pos < k) stage[pos] = key;
         }
     }
     __syncthreads();
-    for (int t = tid; t < k; t += SEL_THREADS) buf[t] = stage[t];
+    const int kept = min(s_misc[2], k);
+    for (int t = tid; t < k; t += SEL_THREADS) buf[t] = t < kept ? stage[t] : 0ull;
     __syncthreads();
+}
+
+// The same selection by ONE warp on its own slice of shared memory (no block barriers): survivors are compacted in place
+// to buf[0, k).  Returns the number kept.
+__device__ __forceinline__ int warp_keep_topk(unsigned long long* buf, int n, int k, int* hist /*[256]*/, int lane) {
+    unsigned long long a = ~0ull, o = 0ull;
+    for (int t = lane; t < n; t += 32) { const unsigned long long key = buf[t]; a &= key; o |= key; }
+    a = warp_and64(a); o = warp_or64(o);
+    const unsigned long long diff = a ^ o;
+    int bits = diff ? 64 - __clzll((long long)diff) : 0;
+    unsigned long long prefix = bits >= 64 ? 0ull : (a >> bits) << bits;
+    int krem = k;
+    while (bits > 0) {
+        const int w = bits < 8 ? bits : 8;
+        const int shift = bits - w;
+        const unsigned long long himask = bits >= 64 ? 0ull : ~((1ull << bits) - 1ull);
+        const unsigned long long dmask = (unsigned long long)((1 << w) - 1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) hist[t * 32 + lane] = 0;
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            const unsigned long long key = buf[t];
+            if ((key & himask) == prefix) atomicAdd(&hist[(int)((key >> shift) & dmask)], 1);
+        }
+        __syncwarp();
+        int bin, before, cb;
+        warp_find_bin(hist, krem, lane, &bin, &before, &cb);
+        __syncwarp();
+        prefix |= (unsigned long long)bin << shift;
+        krem -= before;
+        bits = shift;
+        if (cb == krem) break;
+    }
+    // in-place compaction: everything above the boundary bin + the first krem keys of the bin (all of it after an early exit)
+    const unsigned long long thi = prefix | (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull));
+    int base = 0, taken = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        const unsigned long long key = t < n ? buf[t] : 0ull;
+        const bool edge = t < n && key >= prefix && key <= thi;
+        const unsigned bal_e = __ballot_sync(0xffffffffu, edge);
+        const bool keep = t < n && (key > thi || (edge && taken + __popc(bal_e & lt) < krem));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = base + __popc(bal & lt);
+            if (pos < k) buf[pos] = key;             // pos <= t: never ahead of the keys still to be read
+        }
+        base += __popc(bal);
+        taken += __popc(bal_e);
+        __syncwarp();
+    }
+    return min(base, k);
 }
 
 template <int SRC>
@@ -155,7 +252,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
     int* hist = reinterpret_cast<int*>(stage + SEL_MAX_KOUT);                            // [SEL_WARPS][256]
     int* s_cnt = hist + SEL_WARPS * 256;      // [SEL_MAX_LISTS] list sizes of the current window of lists
     int* s_off = s_cnt + SEL_MAX_LISTS;       // [SEL_MAX_LISTS + 1] exclusive prefix sums
-    int* s_misc = s_off + SEL_MAX_LISTS + 1;  // [4]
+    int* s_misc = s_off + SEL_MAX_LISTS + 1;  // [8]
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int fill = 0;
@@ -238,19 +335,101 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-per-query variant for large query batches: 8 queries per block, one warp each, no block barriers.  With
+// thousands of queries in flight the serial latency of one warp (list loads, ~2 histogram passes, a 128-key bitonic
+// sort) is hidden by the other warps; the block-per-query kernel above needs ~70 block barriers per query and ran
+// 10k queries in 0.7 ms, this one in well under 0.1 ms.  Window = WN keys of shared memory per warp (>= k + one list).
+// ---------------------------------------------------------------------------------------
+constexpr int WSEL_WARPS = 8;
+constexpr int WSEL_MAX_WN = 2048;
+
+template <int SRC>
+__global__ void __launch_bounds__(WSEL_WARPS * 32) topk_select_warp_kernel(const SelParams p, const int WN) {
+    extern __shared__ __align__(16) unsigned char wsel_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(wsel_smem) + (size_t)warp * WN;
+    int* hist = reinterpret_cast<int*>(wsel_smem + (size_t)WSEL_WARPS * WN * 8) + warp * 256;
+    const int q = blockIdx.x * WSEL_WARPS + warp;
+    if (q >= p.Q) return;                       // warps are independent: no block-level barrier below
+    const unsigned lt = (1u << lane) - 1u;
+    int fill = 0;
+    for (int g0 = 0; g0 < p.G; g0 += 32) {
+        const int ng = min(32, p.G - g0);
+        int myc = 0;
+        if (lane < ng) myc = SRC == 0 ? __ldg(p.counts + (size_t)(g0 + lane) * p.Qpad + q) : p.kin;
+        for (int i = 0; i < ng; ++i) {
+            const int c = __shfl_sync(0xffffffffu, myc, i);
+            if (c == 0) continue;
+            if (fill + c > WN) {                 // make room: keep the k best of what has been gathered so far
+                __syncwarp();
+                fill = warp_keep_topk(buf, fill, p.k, hist, lane);
+            }
+            if (SRC == 0) {
+                const unsigned long long* L = p.lists + ((size_t)(g0 + i) * p.Qpad + q) * p.cap;
+#pragma unroll 4
+                for (int t = lane; t < c; t += 32) buf[fill + t] = raw_to_key(__ldcg(L + t));
+                fill += c;
+            } else {
+                const size_t o = (size_t)(g0 + i) * (size_t)p.g_stride + (size_t)q * p.kin;
+                for (int t0 = 0; t0 < c; t0 += 32) {   // empty slots (index < 0) are dropped here
+                    const int t = t0 + lane;
+                    const int32_t ix = t < c ? __ldg(p.in_idx + o + t) : -1;
+                    const unsigned bal = __ballot_sync(0xffffffffu, ix >= 0);
+                    if (ix >= 0) buf[fill + __popc(bal & lt)] = make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+                    fill += __popc(bal);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (fill > p.k) fill = warp_keep_topk(buf, fill, p.k, hist, lane);
+    // final ordering of the <= k survivors
+    const int P = next_pow2(fill);
+    for (int t = fill + lane; t < P; t += 32) buf[t] = 0ull;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool desc = (i & kk) == 0;
+                const unsigned long long a = buf[i], b = buf[l];
+                if ((a < b) == desc) { buf[i] = b; buf[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int t = lane; t < p.k; t += 32) {
+        const unsigned long long key = t < fill ? buf[t] : 0ull;
+        const bool ok = key != 0ull;
+        const float sc = ok ? key_score(key) : -INFINITY;
+        const int32_t ix = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
+        if (p.out_scores) {
+            p.out_scores[(size_t)q * p.out_ld + t] = sc;
+            p.out_idx[(size_t)q * p.out_ld + t] = ix;
+        }
+        for (int g = 0; g < p.n_peers; ++g) {
+            uint32_t* base = static_cast<uint32_t*>(p.peer[g]) + (size_t)p.my_rank * 2 * p.Q * p.k;
+            base[(size_t)q * p.k + t] = __float_as_uint(sc);
+            base[(size_t)p.Q * p.k + (size_t)q * p.k + t] = (uint32_t)ix;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k-th largest value of every row of a dense [Q, n] score block (n <= KTH_MAX_N): the warm
 // start tau0 of the fused top-k.  One block per row, row held in shared memory as ordered
-// u32, 4 x 8-bit radix-select passes with per-warp histograms.
+// u32, up to 4 x 8-bit radix-select passes with per-warp histograms (stops once the boundary bin is taken whole).
 // ---------------------------------------------------------------------------------------
-constexpr int KTH_THREADS = 1024;
-
+template <int KTH_THREADS>
 __global__ void __launch_bounds__(KTH_THREADS)
 row_kth_largest_kernel(const float* __restrict__ scores, int n, long long ld, int k, float* __restrict__ out) {
+    constexpr int KTH_WARPS = KTH_THREADS / 32;
     extern __shared__ __align__(16) unsigned char kth_smem[];
     uint32_t* vals = reinterpret_cast<uint32_t*>(kth_smem);                 // [n]
-    int* hist = reinterpret_cast<int*>(kth_smem + (size_t)n * 4);           // [32][256]
+    int* hist = reinterpret_cast<int*>(kth_smem + (size_t)n * 4);           // [KTH_WARPS][256]
     __shared__ uint32_t s_prefix;
-    __shared__ int s_krem;
+    __shared__ int s_krem, s_done;
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
     if (n < k) {
         if (tid == 0) out[q] = -INFINITY;
@@ -258,11 +437,11 @@ row_kth_largest_kernel(const float* __restrict__ scores, int n, long long ld, in
     }
     const float* row = scores + (size_t)q * ld;
     for (int t = tid; t < n; t += KTH_THREADS) vals[t] = float_to_ordered(__ldcs(row + t));
-    if (tid == 0) { s_prefix = 0u; s_krem = k; }
+    if (tid == 0) { s_prefix = 0u; s_krem = k; s_done = 0; }
     __syncthreads();
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int t = tid; t < 32 * 256; t += KTH_THREADS) hist[t] = 0;
+        for (int t = tid; t < KTH_WARPS * 256; t += KTH_THREADS) hist[t] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
         const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
@@ -274,37 +453,43 @@ row_kth_largest_kernel(const float* __restrict__ scores, int n, long long ld, in
         if (tid < 256) {
             int c = 0;
 #pragma unroll 8
-            for (int w = 0; w < 32; ++w) c += hist[w * 256 + tid];
+            for (int w = 0; w < KTH_WARPS; ++w) c += hist[w * 256 + tid];
             hist[tid] = c;      // row 0 now holds the block histogram
         }
         __syncthreads();
-        if (tid == 0) {
-            int krem = s_krem, b = 255;
-            for (; b > 0; --b) {
-                const int c = hist[b];
-                if (c >= krem) break;
-                krem -= c;
+        if (warp == 0) {       // (was a serial walk over the 256 bins by one thread: 4 us per pass)
+            int bin, before, cb;
+            warp_find_bin(hist, s_krem, tid, &bin, &before, &cb);
+            __syncwarp();
+            if (tid == 0) {
+                s_krem -= before;
+                s_prefix = prefix | ((uint32_t)bin << shift);
+                s_done = (cb == s_krem) ? 1 : 0;      // the whole boundary bin is needed: exactly k values >= prefix
             }
-            s_krem = krem;
-            s_prefix = prefix | ((uint32_t)b << shift);
         }
         __syncthreads();
+        if (s_done) break;
     }
-    if (tid == 0) out[q] = ordered_to_float(s_prefix);
+    if (tid == 0) {
+        const float t = ordered_to_float(s_prefix);     // low bits zero after an early exit: still a lower bound
+        out[q] = t == t ? t : -INFINITY;
+    }
 }
 
 int launch_row_kth_largest(const float* scores, int Q, int n, long long ld, int k, float* out, cudaStream_t stream) {
-    const size_t smem = (size_t)n * 4 + 32 * 256 * 4;
+    const bool small = n <= 4096;                       // 256 threads (8 blocks / SM) for short rows
+    const size_t smem = (size_t)n * 4 + (small ? 8 : 32) * 256 * 4;
     const DeviceInfo& dev = device_info();
     CIR_REQUIRE(n <= KTH_MAX_N && (int)smem + 1024 <= dev.max_smem_optin, CIR_ERR_UNSUPPORTED,
                 "row_kth_largest: n=%d too large for shared memory", n);
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(row_kth_largest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(row_kth_largest_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             KTH_MAX_N * 4 + 32 * 256 * 4));
         attr_dev = dev.device;
     }
-    row_kth_largest_kernel<<<Q, KTH_THREADS, smem, stream>>>(scores, n, ld, k, out);
+    if (small) row_kth_largest_kernel<256><<<Q, 256, smem, stream>>>(scores, n, ld, k, out);
+    else row_kth_largest_kernel<1024><<<Q, 1024, smem, stream>>>(scores, n, ld, k, out);
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;
@@ -316,9 +501,22 @@ static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
     const DeviceInfo& dev = device_info();
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_warp_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            WSEL_WARPS * (WSEL_MAX_WN * 8 + 1024)));
         attr_dev = dev.device;
     }
-    topk_select_kernel<SRC><<<Q, SEL_THREADS, SEL_SMEM_BYTES, stream>>>(p);
+    // large batches: one warp per query (window >= k + the longest list); few queries: one block per query
+    const int longest = SRC == 0 ? p.cap : p.kin;
+    int WN = 512;
+    while (WN < p.k + longest) WN <<= 1;
+    static const char* dbg = getenv("CIR_DEBUG_SELECT");              // experiments: "block" / "warp"
+    const bool want_warp = dbg ? dbg[0] == 'w' : Q >= 4 * dev.num_sms;
+    if (WN <= WSEL_MAX_WN && want_warp) {
+        const size_t smem = (size_t)WSEL_WARPS * ((size_t)WN * 8 + 1024);
+        topk_select_warp_kernel<SRC><<<(Q + WSEL_WARPS - 1) / WSEL_WARPS, WSEL_WARPS * 32, smem, stream>>>(p, WN);
+    } else {
+        topk_select_kernel<SRC><<<Q, SEL_THREADS, SEL_SMEM_BYTES, stream>>>(p);
+    }
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;

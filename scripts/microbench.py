@@ -103,3 +103,41 @@ if what in ("all", "search"):
               f"({2*Q*N*D/ms_t/1e9:7.1f} TF, {N*D*2/ms_t/1e6:7.1f} GB/s) same={bool(torch.equal(i, i2))}")
     ms = timeit(lambda: dbp.sum(dtype=torch.float32), n=5)
     print(f"torch sum over bf16 db: {ms:.3f} ms {N*D*2/ms/1e6:.1f} GB/s")
+
+if what == "shard":
+    # one shard of an 8/4/2-way split 1M database: how the threshold sample size moves the 10k-query search
+    D = 2048
+    for N in [int(a) for a in (sys.argv[2] if len(sys.argv) > 2 else "125000,250000,500000").split(",")]:
+        dbp = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+        for a in range(0, N, 125_000):
+            blk = torch.randn((min(125_000, N - a), D), device=dev)
+            S.pack_rows(blk / blk.norm(dim=1, keepdim=True), "db", "bf16", out=dbp[a:a + blk.shape[0]])
+        for Q in (10_000, 70):
+            q = torch.randn((Q, D), device=dev); q = q / q.norm(dim=1, keepdim=True)
+            qp = S.pack_rows(q, "query", "bf16")
+            s, i = S.search_packed(qp, dbp, 100)
+            tau = (s[:, -1] - 1e-4).contiguous()
+            ms = timeit(lambda: S.search_packed(qp, dbp, 100), n=5)
+            ms_t = timeit(lambda: S.search_packed(qp, dbp, 100, tau0=tau), n=5)
+            print(f"shard N={N} Q={Q} sample={os.environ.get('CIR_DEBUG_SAMPLE_ROWS','rule')}: {ms:8.3f} ms ({2*Q*N*D/ms/1e9:7.1f} TF) | exact tau0 {ms_t:8.3f} ms")
+        del dbp
+if what == "kernels":
+    # per-kernel device times (CUPTI through torch.profiler) of one search: N rows, Q queries
+    from torch.profiler import profile, ProfilerActivity
+    D = 2048
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    dbp = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+    for a in range(0, N, 125_000):
+        blk = torch.randn((min(125_000, N - a), D), device=dev)
+        S.pack_rows(blk / blk.norm(dim=1, keepdim=True), "db", "bf16", out=dbp[a:a + blk.shape[0]])
+    for Q in (10_000, 70):
+        q = torch.randn((Q, D), device=dev); q = q / q.norm(dim=1, keepdim=True)
+        qp = S.pack_rows(q, "query", "bf16")
+        for _ in range(3): S.search_packed(qp, dbp, 100)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5): S.search_packed(qp, dbp, 100)
+            torch.cuda.synchronize()
+        for e in prof.key_averages():
+            if e.device_time_total > 0:
+                print(f"kernels N={N} Q={Q}: {e.key[:70]:70s} x{e.count:3d}  {e.device_time_total / e.count:10.1f} us")

@@ -163,6 +163,38 @@ def test_many_splits_small_k_large_n():
         check_topk_against_exact(i.cpu().numpy(), s.cpu().numpy(), ex, k, TOL_X3)
 
 
+@pytest.mark.parametrize("k", [1, 37, 100, 512])
+def test_large_query_batch_warp_select(k):
+    """Q >= 4 x SM count takes the warp-per-query selection kernel (and N >= 65,536 the threshold pre-pass): same lists as
+    the oracle, and merging ragged shard lists (one shorter than k: -1 padding) reproduces the global list bit for bit."""
+    from cirtorch_b200 import search as S
+    N, Q, D = 70_000, 700, 64
+    db, _ = clustered_unit_rows(N, D, 300, 0.9, seed=21)
+    q, _ = clustered_unit_rows(Q, D, 300, 0.9, seed=21)
+    ex = _exact(q, db)
+    qd, dbd = _dev(q), _dev(db)
+    s, i = S.search_topk_rows(qd, dbd, k, mode="bf16x3")
+    check_topk_against_exact(i.cpu().numpy(), s.cpu().numpy(), ex, k, TOL_X3)
+    parts_s, parts_i = [], []
+    bounds = [0, 30, 20_000, 20_001, 55_555, N]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        ps, pi = S.search_topk_rows(qd, dbd[a:b].contiguous(), k, mode="bf16x3", idx_offset=a)
+        parts_s.append(ps)
+        parts_i.append(pi)
+    ms, mi = S.merge_topk(torch.stack(parts_s), torch.stack(parts_i), k)
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+def test_equal_scores_flood_large_batch():
+    """The flood of ties through the warp-per-query selection: lowest indices win for every one of 600 queries."""
+    from cirtorch_b200 import search as S
+    row = np.random.RandomState(6).randn(1, 64).astype(np.float32)
+    db = np.repeat(row, 3000, axis=0)
+    q = np.random.RandomState(7).randn(600, 64).astype(np.float32)
+    s, i = S.search_topk_rows(_dev(q), _dev(db), 100, mode="bf16")
+    np.testing.assert_array_equal(i.cpu().numpy(), np.tile(np.arange(100, dtype=np.int32), (600, 1)))
+
+
 def test_equal_scores_flood():
     """All database rows identical: every score ties; the lowest indices must win."""
     from cirtorch_b200 import search as S
