@@ -215,6 +215,78 @@ def descriptor_tail(x, p=None, eps=1e-6, weight=None, bias=None, pooling="GeM", 
     return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
 
 
+def rmac_grid(H, W, L=3):
+    """Per level l = 1..L of the R-MAC grid: (wl, cenH, cenW) = region side, top rows, left columns
+    (cirtorch/modules/pools.py:126-160 / :64-103).  Six-element HOST arithmetic, done with the same float32 torch
+    ops in the same order as the reference so that near-ties (e.g. an 11 x 47 map) round the same way."""
+    import math
+    short, long_ = min(W, H), max(W, H)
+    n_extra = torch.tensor([2., 3., 4., 5., 6., 7.])          # candidate region counts along the long side
+    stride = (long_ - short) / (n_extra - 1)
+    overlap = (short ** 2 - short * stride) / short ** 2
+    best = int(torch.min(torch.abs(overlap - 0.4), 0)[1])      # desired overlap of neighbouring regions: 0.4
+    Wd = best + 1 if H < W else 0
+    Hd = best + 1 if H > W else 0
+    levels = []
+    for l in range(1, L + 1):
+        wl = math.floor(2 * short / (l + 1))
+        wl2 = math.floor(wl / 2 - 1)
+
+        def starts(extent, extra):
+            n = l + extra
+            step = 0 if n == 1 else (extent - wl) / (n - 1)
+            return (torch.floor(wl2 + torch.arange(n, dtype=torch.float32) * step).int() - wl2).tolist()
+
+        levels.append((int(wl), starts(H, Hd), starts(W, Wd)))
+    return levels
+
+
+def rmac_regions(H, W, L=3):
+    """All regions of Rpool.roipool in its order (levels, rows outer / columns inner) as (row0, col0, height, width);
+    the whole map (roipool's first vector) is NOT included."""
+    return [(i, j, wl, wl) for (wl, cenH, cenW) in rmac_grid(H, W, L) if wl > 0 for i in cenH for j in cenW]
+
+
+def region_pool(x, regions, p=None, eps=1e-6, pooling="GeM"):
+    """Pool every (row0, col0, height, width) region of an N x C x H x W map in ONE pass over the map
+    (cir_region_pool) -> N x R x C.  ``pooling`` / ``p`` / ``eps`` as in descriptor_tail."""
+    import ctypes as C
+    if pooling not in _POOL:
+        raise KeyError(pooling)
+    _lib.require_cuda(x, p if torch.is_tensor(p) else None)
+    lib = _lib.load()
+    x = _as_f32_contig(x)
+    if x.dim() != 4:
+        raise ValueError("expected an N x C x H x W feature map, got shape %s" % (tuple(x.shape),))
+    N, Cc, H, W = x.shape
+    R = len(regions)
+    if R < 1:
+        raise ValueError("region_pool needs at least one region")
+    p_stride = 0
+    if pooling in ("GeM", "GeMmp"):
+        if p is None:
+            raise ValueError("GeM pooling needs the exponent p")
+        if not torch.is_tensor(p):
+            p = torch.full((1,), float(p), dtype=torch.float32, device=x.device)
+        p = p.detach().reshape(-1).float().contiguous()
+        if p.numel() not in (1, Cc):
+            raise ValueError("GeM exponent must have 1 or C=%d elements, got %d" % (Cc, p.numel()))
+        p_stride = 0 if p.numel() == 1 else 1
+    else:
+        p = None
+    flat = []
+    for r in regions:
+        if len(r) != 4:
+            raise ValueError("a region is (row0, col0, height, width)")
+        flat.extend(int(v) for v in r)
+    reg = (C.c_int32 * len(flat))(*flat)
+    out = torch.empty((N, R, Cc), dtype=torch.float32, device=x.device)
+    rc = lib.cir_region_pool(_lib.ptr(x), N, Cc, H, W, C.cast(reg, C.c_void_p), R, _lib.ptr(p), p_stride, float(eps),
+                             _POOL[pooling], _lib.ptr(out), _lib.stream_of(x))
+    _lib.check(rc, "cir_region_pool")
+    return out
+
+
 def gem(x, p=3, eps=1e-6):
     """GeM pooling, cirtorch/modules/pools.py:37-38 -> N x C x 1 x 1."""
     return descriptor_tail(x, p=p, eps=eps, pooling="GeM", pool_only=True)[:, :, None, None]

@@ -102,6 +102,13 @@ int cir_bias_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, const float
 /* PowerLaw.forward (cirtorch/modules/normalizations.py:19-27): out = sign(x + eps) * sqrt(|x + eps|), elementwise */
 int cir_powerlaw(const float* x, int64_t n, float eps, float* out, void* stream);
 
+/* Regional pooling: replaces the region loop of Rpool.roipool (cirtorch/modules/pools.py:126-167) and the max-pools of
+ * RMAC.forward (pools.py:64-113).  x [N, C, H, W] fp32 device (read once); regions [R][4] int32 in HOST memory =
+ * (row0, col0, height, width) of every region (inside the map, R <= 64); pool_mode / p / p_stride / eps as in
+ * cir_tail_fwd, applied per region; out [N][R][C] fp32 device (row = one region descriptor). */
+int cir_region_pool(const float* x, int N, int C, int H, int W, const int32_t* regions, int R,
+                    const float* p, int p_stride, float eps, int pool_mode, float* out, void* stream);
+
 /* row-wise L2N in place or out of place: L2N.forward on [N, C] rows (normalizations.py:15) */
 int cir_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, float eps,
                  float* out, int64_t out_ld, void* stream);

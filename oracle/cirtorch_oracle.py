@@ -13,7 +13,7 @@ and no golden vectors, so parity is pinned by running the
 ``tests/test_oracle_golden.py`` checks this oracle against those fixtures.
 
 Parity status
-  * tail (GeM / MAC / SPoC / L2N / globalHead), whitenapply / whitenlearn /
+  * tail (GeM / MAC / SPoC / L2N / globalHead), regional pooling (Rpool / RMAC), whitenapply / whitenlearn /
     pcawhitenlearn / cholesky, compute_ap / compute_map, multi-scale mean:
     PINNED by fixtures generated from the imported reference code.
   * ranking (scripts/train_globalF.py:733-734) and hard-negative mining
@@ -88,6 +88,72 @@ def head_forward(x, p=3.0, eps=1e-6, weight=None, bias=None, do_whitening=True,
             v = v + bias
         v = l2n(v, l2_eps)
     return v.t()
+
+
+def rmac_region_grid(H: int, W: int, L: int = 3):
+    """Region grid shared by Rpool.roipool (cirtorch/modules/pools.py:126-165) and RMAC.forward (:64-103).
+
+    Returns one (wl, tops, lefts) triple per level l = 1..L.  The number of extra regions along the long side is the
+    candidate in {2..7} whose neighbour overlap is closest to 0.4 (:127-145); level l has side wl = floor(2 w / (l + 1))
+    and its top-left corners are floor(wl2 + i * b) - wl2 with b = (extent - wl) / (count - 1) (:150-160).  float32
+    torch arithmetic as in the reference (the 0.4 comparison has near-ties, e.g. 11 x 47)."""
+    import math
+    w = min(W, H)
+    steps = torch.Tensor([2, 3, 4, 5, 6, 7])
+    b = (max(H, W) - w) / (steps - 1)
+    idx = torch.min(torch.abs(((w ** 2 - w * b) / w ** 2) - 0.4), 0)[1].item()
+    Wd, Hd = (idx + 1, 0) if H < W else ((0, idx + 1) if H > W else (0, 0))
+    out = []
+    for l in range(1, L + 1):
+        wl = math.floor(2 * w / (l + 1))
+        wl2 = math.floor(wl / 2 - 1)
+        bw = 0 if l + Wd == 1 else (W - wl) / (l + Wd - 1)
+        bh = 0 if l + Hd == 1 else (H - wl) / (l + Hd - 1)
+        lefts = (torch.floor(wl2 + torch.Tensor(range(l + Wd)) * bw).int() - wl2).tolist()
+        tops = (torch.floor(wl2 + torch.Tensor(range(l + Hd)) * bh).int() - wl2).tolist()
+        out.append((wl, tops, lefts))
+    return out
+
+
+def rpool_forward(x: torch.Tensor, pool, whiten_weight=None, whiten_bias=None, L: int = 3, aggregate: bool = True,
+                  l2_eps: float = 1e-6) -> torch.Tensor:
+    """Rpool.forward, cirtorch/modules/pools.py:169-197: ``pool`` (a callable N x C x h x w -> N x C x 1 x 1) over the
+    whole map and every grid region (roipool :126-167), L2N per region, optional Linear + L2N per region, sum over
+    regions, L2N.  Returns N x D x 1 x 1 (aggregate) or N x R x D x 1 x 1."""
+    N, _, H, W = x.shape
+    vecs = [pool(x)]
+    for wl, tops, lefts in rmac_region_grid(H, W, L):
+        if wl == 0:
+            continue
+        for i in tops:
+            for j in lefts:
+                vecs.append(pool(x[:, :, i:i + wl, j:j + wl]))
+    o = torch.stack([v.reshape(N, -1) for v in vecs], dim=1)            # N x R x C
+    R = o.shape[1]
+    o = l2n(o.reshape(N * R, -1), l2_eps)
+    if whiten_weight is not None:
+        o = torch.nn.functional.linear(o, whiten_weight, whiten_bias)
+        o = l2n(o, l2_eps)
+    o = o.reshape(N, R, -1)
+    if aggregate:
+        return l2n(o.sum(dim=1), l2_eps)[:, :, None, None]
+    return o[:, :, :, None, None]
+
+
+def rmac_forward(x: torch.Tensor, L: int = 3, eps: float = 1e-6) -> torch.Tensor:
+    """RMAC.forward AS WRITTEN, cirtorch/modules/pools.py:64-113.  The loops over the region centres (:105-113) sit
+    outside the level loop and the pooling statements outside the column loop, so what is computed is
+    L2N(MAC(x)) + sum over the rows i of level L of L2N(MAC(x[.., i:i+wl, j:j+wl])) with j = the LAST column centre
+    of level L.  (L = 1 with H >= W leaves ``cenW`` undefined in the reference -> NameError.)"""
+    N, C, H, W = x.shape
+    if L == 1 and not H < W:
+        raise NameError("cenW")
+    v = l2n(mac(x), eps)
+    wl, tops, lefts = rmac_region_grid(H, W, L)[-1]
+    j = lefts[-1]
+    for i in tops:
+        v = v + l2n(mac(x[:, :, i:i + wl, j:j + wl]), eps)
+    return v
 
 
 def multiscale_mean(desc_per_scale) -> torch.Tensor:

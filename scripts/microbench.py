@@ -141,3 +141,24 @@ if what == "kernels":
         for e in prof.key_averages():
             if e.device_time_total > 0:
                 print(f"kernels N={N} Q={Q}: {e.key[:70]:70s} x{e.count:3d}  {e.device_time_total / e.count:10.1f} us")
+if what == "regions":
+    from cirtorch_b200.modules.pools import GeM, MAC, Rpool
+    B, C, H, W = 64, 2048, 32, 32
+    xs = [torch.relu(torch.randn((B, C, H, W), device=dev)) for _ in range(2)]
+    i = [0]
+    def nxt():
+        i[0] ^= 1; return xs[i[0]]
+    regs = [(0, 0, H, W)] + LF.rmac_regions(H, W, 3)
+    p3 = torch.full((1,), 3.0, device=dev); p27 = torch.full((1,), 2.7, device=dev)
+    gb = B * C * H * W * 4 / 1e6
+    lin = torch.nn.Linear(C, C).to(dev)
+    rp = Rpool(GeM(p=3), whiten=lin, L=3).to(dev)
+    with torch.no_grad():
+        for name, fn in [
+            ("region_pool GeM p=3 (%d regions)" % len(regs), lambda: LF.region_pool(nxt(), regs, p=p3, pooling="GeM")),
+            ("region_pool GeM p=2.7", lambda: LF.region_pool(nxt(), regs, p=p27, pooling="GeM")),
+            ("region_pool MAC", lambda: LF.region_pool(nxt(), regs, pooling="MAC")),
+            ("Rpool(GeM)+whiten+aggregate", lambda: rp(nxt())),
+        ]:
+            ms = timeit(fn)
+            print(f"regions {name:36s} {ms*1e3:8.1f} us  {gb/ms:8.1f} GB/s(x only)")

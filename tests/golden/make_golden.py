@@ -177,13 +177,57 @@ def multiscale_fixture():
                         preds=torch.stack(preds).numpy(), out=pred.numpy())
 
 
+def regional_fixtures():
+    """Rpool / RMAC (cirtorch/modules/pools.py:57-197), run from the imported reference."""
+    from cirtorch.modules.pools import GeM, MAC, SPoC, RMAC, Rpool
+
+    g = torch.Generator().manual_seed(4321)
+    cases = {}
+    shapes = {"sq": (2, 16, 12, 12), "wide": (3, 16, 9, 14), "tall": (2, 8, 17, 10), "tiny": (1, 8, 5, 5)}
+    with torch.no_grad():
+        for name, shp in shapes.items():
+            x = torch.relu(torch.randn(*shp, generator=g))
+            x[0, 0] = 0.0
+            cases[f"{name}_x"] = x.numpy()
+            C = shp[1]
+            lin = torch.nn.Linear(C, C)          # Rpool.forward views the result back as C-dimensional (:190)
+            lin.weight.copy_(0.3 * torch.randn(C, C, generator=g))
+            lin.bias.copy_(0.05 * torch.randn(C, generator=g))
+            cases[f"{name}_W"] = lin.weight.numpy().copy()
+            cases[f"{name}_b"] = lin.bias.numpy().copy()
+            for L in (1, 2, 3):
+                cases[f"{name}_gem3_L{L}"] = Rpool(GeM(p=3), L=L)(x).numpy()
+                cases[f"{name}_gem25_white_L{L}"] = Rpool(GeM(p=2.5), whiten=lin, L=L)(x).numpy()
+                cases[f"{name}_mac_L{L}"] = Rpool(MAC(), L=L)(x).numpy()
+                cases[f"{name}_spoc_regions_L{L}"] = Rpool(SPoC(), L=L)(x, aggregate=False).numpy()
+                try:
+                    cases[f"{name}_rmac_L{L}"] = RMAC(L=L)(x).numpy()
+                except NameError:      # pools.py:94-98: cenW never assigned when L + Wd == 1
+                    cases[f"{name}_rmac_L{L}"] = np.zeros(0, dtype=np.float32)
+    # the region grid itself, recovered from the reference by pooling a position-coded map
+    grid = []
+    for (H, W, L) in [(12, 12, 3), (9, 14, 3), (17, 10, 2), (11, 47, 3), (47, 11, 4), (32, 32, 3), (24, 32, 3), (5, 5, 3), (1, 7, 2)]:
+        xpos = torch.arange(H * W, dtype=torch.float32).view(1, 1, H, W)
+        rec = []
+
+        def probe(t, rec=rec, W=W):
+            v = int(t[0, 0, 0, 0].item())
+            rec.append((v // W, v % W, t.shape[2], t.shape[3]))
+            return torch.zeros(1, 1, 1, 1)
+
+        Rpool(probe, L=L).roipool(xpos, probe, L=L)
+        for r in rec:
+            grid.append((H, W, L) + r)
+    cases["grid"] = np.array(grid, dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "regional.npz"), **cases)
+
+
 if __name__ == "__main__":
     _import_reference()
     torch.set_num_threads(1)
-    tail_fixtures()
-    whiten_fixtures()
-    rank_fixtures()
-    mining_fixtures()
-    eval_fixtures()
-    multiscale_fixture()
+    only = sys.argv[1:]            # e.g. ``make_golden.py regional`` regenerates one fixture file
+    for name, fn in (("tail", tail_fixtures), ("whiten", whiten_fixtures), ("rank", rank_fixtures), ("mining", mining_fixtures),
+                     ("eval", eval_fixtures), ("multiscale", multiscale_fixture), ("regional", regional_fixtures)):
+        if not only or name in only:
+            fn()
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

@@ -93,6 +93,67 @@ def test_pooling_variants():
     assert _rel(out.cpu(), ref) < RTOL
 
 
+def test_regional_pooling_golden(golden):
+    """Rpool / RMAC on the one-pass region kernel vs the fixtures produced by the reference (pools.py:57-197)."""
+    from cirtorch_b200.modules.pools import GeM, MAC, SPoC, RMAC, Rpool, POOLING_LAYERS
+    assert POOLING_LAYERS["RMAC"] is RMAC and POOLING_LAYERS["ROIpool"] is Rpool
+    g = golden("regional")
+    for name in ("sq", "wide", "tall", "tiny"):
+        x = torch.from_numpy(g[f"{name}_x"]).to(DEV)
+        C = x.shape[1]
+        lin = torch.nn.Linear(C, C).to(DEV)
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(g[f"{name}_W"]))
+            lin.bias.copy_(torch.from_numpy(g[f"{name}_b"]))
+            for L in (1, 2, 3):
+                for key, mod, kw in ((f"{name}_gem3_L{L}", Rpool(GeM(p=3), L=L), {}),
+                                     (f"{name}_gem25_white_L{L}", Rpool(GeM(p=2.5), whiten=lin, L=L), {}),
+                                     (f"{name}_mac_L{L}", Rpool(MAC(), L=L), {}),
+                                     (f"{name}_spoc_regions_L{L}", Rpool(SPoC(), L=L), {"aggregate": False})):
+                    out = mod.to(DEV)(x, **kw)
+                    want = torch.from_numpy(g[key])
+                    assert out.shape == want.shape, key
+                    D = want.shape[-3]           # per-descriptor relative error (north-star bar), elementwise with a floor
+                    assert _rel(out.cpu().reshape(-1, D), want.reshape(-1, D), dim=1) < RTOL, key
+                    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-3, atol=2e-6, err_msg=key)
+                want = g[f"{name}_rmac_L{L}"]
+                if want.size == 0:
+                    with pytest.raises(NameError):
+                        RMAC(L=L)(x)
+                else:
+                    out = RMAC(L=L)(x)
+                    assert out.shape == want.shape
+                    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+
+
+def test_regional_pooling_vs_oracle_layer4_shape():
+    """ResNet layer-4 sized maps (2048 x 32 x 32 and a non-square 24 x 40), per-channel exponents, a generic rpool callable."""
+    from cirtorch_b200.modules.pools import GeM, GeMmp, Rpool
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(3)
+    for shape in ((3, 2048, 32, 32), (2, 256, 24, 40)):
+        x = torch.relu(torch.randn(*shape))
+        C = shape[1]
+        lin = torch.nn.Linear(C, C)
+        ref = O.rpool_forward(x, lambda t: O.gem(t, 3.0), lin.weight.detach(), lin.bias.detach(), L=3)
+        with torch.no_grad():
+            out = Rpool(GeM(p=3), whiten=lin.to(DEV), L=3).to(DEV)(x.to(DEV))
+        assert _rel(out.cpu().reshape(shape[0], C).t(), ref.reshape(shape[0], C).t()) < RTOL
+        pc = 2.0 + 2.0 * torch.rand(C)
+        ref = O.rpool_forward(x, lambda t: O.gem(t, pc), L=2)
+        mp = GeMmp(p=3, mp=C)
+        with torch.no_grad():
+            mp.p.copy_(pc)
+            out = Rpool(mp.to(DEV), L=2)(x.to(DEV))
+            # any other callable takes the region-by-region composition
+            out2 = Rpool(lambda t: LF.gem(t, p=3.0), L=2)(x.to(DEV))
+        assert _rel(out.cpu().reshape(shape[0], C).t(), ref.reshape(shape[0], C).t()) < RTOL
+        ref2 = O.rpool_forward(x, lambda t: O.gem(t, 3.0), L=2)
+        assert _rel(out2.cpu().reshape(shape[0], C).t(), ref2.reshape(shape[0], C).t()) < RTOL
+    with pytest.raises(ValueError):
+        LF.region_pool(torch.zeros(1, 4, 8, 8, device=DEV), [(0, 0, 9, 8)], pooling="MAC")
+
+
 def test_state_dict_keys_and_empty_batch():
     head = _head(64)
     assert set(head.state_dict().keys()) == {"pool.p", "whiten.weight", "whiten.bias"}

@@ -105,3 +105,12 @@ def test_store_formats_roundtrip(tmp_path):
     torch.save({"config": "", "state_dict": {"ret_head": sd, "body": {}}, "training_meta": {"epoch": 7}}, tmp_path / "snap.pth")
     meta = store.load_ret_head(str(tmp_path / "snap.pth"), head)
     assert meta["epoch"] == 7 and float(head.pool.p) == 4.0 and float(head.whiten.bias.abs().max()) == 0.0
+
+
+def test_rmac_region_grid_matches_fixture(golden):
+    """Host logic of the regional pooling: the product's region grid == the grid recovered from the reference."""
+    from cirtorch_b200 import functional as LF
+    grid = golden("regional")["grid"].tolist()
+    for (H, W, L) in sorted({tuple(r[:3]) for r in grid}):
+        want = [tuple(r[3:]) for r in grid if tuple(r[:3]) == (H, W, L)]
+        assert [(0, 0, H, W)] + LF.rmac_regions(H, W, L) == want, (H, W, L)

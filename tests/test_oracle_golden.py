@@ -22,6 +22,37 @@ def test_tail_matches_reference(golden):
                                    g[f"{c}_head_nowhiten"], rtol=1e-5, atol=1e-7)
 
 
+def test_regional_pooling_matches_reference(golden):
+    """Rpool / RMAC restatements (and the region grid) against the imported reference (pools.py:57-197)."""
+    g = golden("regional")
+    for name in ("sq", "wide", "tall", "tiny"):
+        x = torch.from_numpy(g[f"{name}_x"])
+        W, b = torch.from_numpy(g[f"{name}_W"]), torch.from_numpy(g[f"{name}_b"])
+        for L in (1, 2, 3):
+            np.testing.assert_allclose(O.rpool_forward(x, lambda t: O.gem(t, 3.0), L=L).numpy(), g[f"{name}_gem3_L{L}"],
+                                       rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(O.rpool_forward(x, lambda t: O.gem(t, 2.5), W, b, L=L).numpy(),
+                                       g[f"{name}_gem25_white_L{L}"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(O.rpool_forward(x, O.mac, L=L).numpy(), g[f"{name}_mac_L{L}"], rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(O.rpool_forward(x, O.spoc, L=L, aggregate=False).numpy(),
+                                       g[f"{name}_spoc_regions_L{L}"], rtol=1e-5, atol=1e-8)
+            want = g[f"{name}_rmac_L{L}"]
+            if want.size == 0:            # the reference raises NameError (cenW never assigned)
+                try:
+                    O.rmac_forward(x, L=L)
+                    raise AssertionError("expected NameError")
+                except NameError:
+                    pass
+            else:
+                np.testing.assert_allclose(O.rmac_forward(x, L=L).numpy(), want, rtol=1e-6, atol=1e-8)
+    grid = g["grid"]
+    for (H, W_, L) in sorted({tuple(r[:3]) for r in grid.tolist()}):
+        want = [tuple(r[3:]) for r in grid.tolist() if tuple(r[:3]) == (H, W_, L)]
+        got = [(0, 0, H, W_)] + [(i, j, wl, wl) for (wl, tops, lefts) in O.rmac_region_grid(H, W_, L) if wl > 0
+                                 for i in tops for j in lefts]
+        assert got == want, (H, W_, L)
+
+
 def test_whiten_matches_reference(golden):
     g = golden("whiten")
     X = g["X"]
