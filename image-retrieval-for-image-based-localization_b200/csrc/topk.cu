@@ -193,9 +193,10 @@ __device__ __forceinline__ void block_keep_topk(unsigned long long* buf, int fil
 
 // The same selection by ONE warp on its own slice of shared memory (no block barriers): survivors are compacted in place
 // to buf[0, k).  Returns the number kept.
-__device__ __forceinline__ int warp_keep_topk(unsigned long long* buf, int n, int k, int* hist /*[256]*/, int lane) {
-    unsigned long long a = ~0ull, o = 0ull;
-    for (int t = lane; t < n; t += 32) { const unsigned long long key = buf[t]; a &= key; o |= key; }
+// ``a`` / ``o``: this lane's AND / OR over (a superset of) the keys it stored -- tracked while the keys are gathered, so no
+// separate pass is needed to find the bits all keys share.
+__device__ __forceinline__ int warp_keep_topk(unsigned long long* buf, int n, int k, int* hist /*[256]*/, int lane,
+                                              unsigned long long a, unsigned long long o, unsigned long long* floor_key) {
     a = warp_and64(a); o = warp_or64(o);
     const unsigned long long diff = a ^ o;
     int bits = diff ? 64 - __clzll((long long)diff) : 0;
@@ -241,6 +242,7 @@ __device__ __forceinline__ int warp_keep_topk(unsigned long long* buf, int n, in
         taken += __popc(bal_e);
         __syncwarp();
     }
+    *floor_key = prefix;          // k keys >= prefix are kept: anything smaller can never enter the top-k again
     return min(base, k);
 }
 
@@ -353,36 +355,89 @@ __global__ void __launch_bounds__(WSEL_WARPS * 32) topk_select_warp_kernel(const
     if (q >= p.Q) return;                       // warps are independent: no block-level barrier below
     const unsigned lt = (1u << lane) - 1u;
     int fill = 0;
+    unsigned long long and_acc = ~0ull, or_acc = 0ull;      // bits shared by every key gathered so far (lane-local)
+    unsigned long long floor_key = 0ull;                    // after a selection: k keys >= floor_key are in the window
+    // Gather in batches of <= 256 entries (8 per lane, all loads of a batch in flight together); the loads of batch
+    // i + 1 are issued BEFORE batch i is written to shared memory, so one warp pays one memory round trip per batch
+    // instead of one per 32 entries.
+    constexpr int BPL = 8;                                  // entries per lane per batch
+    unsigned long long pend[BPL];
+    int pend_n = 0;
+    auto commit = [&]() {                                   // pending batch -> window (making room first)
+        if (pend_n == 0) return;
+        if (fill + pend_n > WN) {
+            __syncwarp();
+            fill = warp_keep_topk(buf, fill, p.k, hist, lane, and_acc, or_acc, &floor_key);
+        }
+        if (SRC == 0 && floor_key == 0ull) {                // first window: everything is stored
+#pragma unroll
+            for (int u = 0; u < BPL; ++u) {
+                const int t = u * 32 + lane;
+                if (t < pend_n) {
+                    const unsigned long long key = raw_to_key(pend[u]);
+                    buf[fill + t] = key;
+                    and_acc &= key; or_acc |= key;
+                }
+            }
+            fill += pend_n;
+        } else {
+            // empty slots (key 0) and, once a selection has run, keys below its k-th best are dropped here: like a
+            // streaming top-k the window then fills ~k ln(n) slowly and one more selection at the end is enough
+#pragma unroll
+            for (int u = 0; u < BPL; ++u) {
+                const int t = u * 32 + lane;
+                unsigned long long key = t < pend_n ? pend[u] : 0ull;
+                if (SRC == 0 && key != 0ull) key = raw_to_key(key);
+                const bool keep = key != 0ull && key >= floor_key;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    buf[fill + __popc(bal & lt)] = key;
+                    and_acc &= key; or_acc |= key;
+                }
+                fill += __popc(bal);
+            }
+        }
+        pend_n = 0;
+    };
     for (int g0 = 0; g0 < p.G; g0 += 32) {
         const int ng = min(32, p.G - g0);
         int myc = 0;
         if (lane < ng) myc = SRC == 0 ? __ldg(p.counts + (size_t)(g0 + lane) * p.Qpad + q) : p.kin;
         for (int i = 0; i < ng; ++i) {
             const int c = __shfl_sync(0xffffffffu, myc, i);
-            if (c == 0) continue;
-            if (fill + c > WN) {                 // make room: keep the k best of what has been gathered so far
-                __syncwarp();
-                fill = warp_keep_topk(buf, fill, p.k, hist, lane);
-            }
-            if (SRC == 0) {
-                const unsigned long long* L = p.lists + ((size_t)(g0 + i) * p.Qpad + q) * p.cap;
-#pragma unroll 4
-                for (int t = lane; t < c; t += 32) buf[fill + t] = raw_to_key(__ldcg(L + t));
-                fill += c;
-            } else {
-                const size_t o = (size_t)(g0 + i) * (size_t)p.g_stride + (size_t)q * p.kin;
-                for (int t0 = 0; t0 < c; t0 += 32) {   // empty slots (index < 0) are dropped here
-                    const int t = t0 + lane;
-                    const int32_t ix = t < c ? __ldg(p.in_idx + o + t) : -1;
-                    const unsigned bal = __ballot_sync(0xffffffffu, ix >= 0);
-                    if (ix >= 0) buf[fill + __popc(bal & lt)] = make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
-                    fill += __popc(bal);
+            for (int b0 = 0; b0 < c; b0 += BPL * 32) {
+                const int nb = min(BPL * 32, c - b0);
+                unsigned long long cur[BPL];
+                if (SRC == 0) {
+                    const unsigned long long* L = p.lists + ((size_t)(g0 + i) * p.Qpad + q) * p.cap + b0;
+#pragma unroll
+                    for (int u = 0; u < BPL; ++u) {
+                        const int t = u * 32 + lane;
+                        cur[u] = t < nb ? __ldcg(L + t) : 0ull;
+                    }
+                } else {
+                    const size_t o = (size_t)(g0 + i) * (size_t)p.g_stride + (size_t)q * p.kin + b0;
+                    int32_t ix[BPL];
+                    float sc[BPL];
+#pragma unroll
+                    for (int u = 0; u < BPL; ++u) {
+                        const int t = u * 32 + lane;
+                        ix[u] = t < nb ? __ldg(p.in_idx + o + t) : -1;
+                        sc[u] = t < nb ? __ldg(p.in_scores + o + t) : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < BPL; ++u) cur[u] = ix[u] < 0 ? 0ull : make_key(sc[u], (uint32_t)ix[u]);
                 }
+                commit();                                   // the previous batch, while this one is in flight
+#pragma unroll
+                for (int u = 0; u < BPL; ++u) pend[u] = cur[u];
+                pend_n = nb;
             }
         }
     }
+    commit();
     __syncwarp();
-    if (fill > p.k) fill = warp_keep_topk(buf, fill, p.k, hist, lane);
+    if (fill > p.k) fill = warp_keep_topk(buf, fill, p.k, hist, lane, and_acc, or_acc, &floor_key);
     // final ordering of the <= k survivors
     const int P = next_pow2(fill);
     for (int t = fill + lane; t < P; t += 32) buf[t] = 0ull;
