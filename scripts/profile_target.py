@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: runs a few launches of one hot kernel at its BASELINE.json size.
-    python scripts/profile_target.py tail|search10k|search70|mining [n_launches]
+    python scripts/profile_target.py tail|search10k|search70|regions|mining [n_launches]
 """
 import os
 import sys
@@ -37,6 +37,13 @@ elif what in ("search10k", "search70"):
         tau = (s0[:, -1] - 1e-4).contiguous()
     for i in range(n):
         S.search_packed(qp, dbp, 100, tau0=tau)
+elif what == "regions":
+    from cirtorch_b200 import functional as LF
+    x = torch.relu(torch.randn((64, 2048, 32, 32), device=dev))
+    regs = [(0, 0, 32, 32)] + LF.rmac_regions(32, 32, 3)
+    p3 = torch.full((1,), 3.0, device=dev)
+    for i in range(n):
+        LF.region_pool(x, regs, p=p3, pooling="GeM")
 elif what == "mining":
     from cirtorch_b200.mining import mine_hard_negatives_rows
     q = torch.randn((2000, 2048), device=dev)
