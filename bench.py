@@ -145,6 +145,9 @@ def dist_env():
     return rank, local, world
 
 
+LAST_PER_RANK_MS = []          # device time of the last timed region on every rank (the reported time is their maximum)
+
+
 def timed_region(fn, steps, warmup, world, sampler=None):
     """W untimed steps, then exactly K timed steps between barrier + synchronize; max over ranks (device time)."""
     import torch.distributed as dist
@@ -169,8 +172,12 @@ def timed_region(fn, steps, warmup, world, sampler=None):
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        LAST_PER_RANK_MS[:] = [float(v) for v in every]
+        ms = max(LAST_PER_RANK_MS)
+    else:
+        LAST_PER_RANK_MS[:] = [ms]
     return ms
 
 
@@ -322,12 +329,13 @@ def bench_search(dev, rank, world, pk, steps, warmup):
         k_steps = max(3, steps // 10) if Q >= 1000 else max(5, steps)
         _lib.launch_count(reset=True)
         ms = timed_region(step, k_steps, max(3, warmup), world) / k_steps
+        per_rank = [round(v / k_steps, 4) for v in LAST_PER_RANK_MS]
         launches = _lib.launch_count()
         ms_kernel = timed_region(step_local, k_steps, 3, world) / k_steps
         flops = 2.0 * Q * n_loc * DB_D
         res = {"queries_per_s": Q / (ms * 1e-3), "ms_per_search": ms, "ms_local_kernels": ms_kernel,
                "steps": k_steps, "launches_per_search": launches // (k_steps + max(3, warmup)), "Q": Q, "N": DB_N, "k": TOPK,
-               "exchange": exchange}
+               "exchange": exchange, "per_rank_ms_per_search": per_rank}
         if Q >= 1000:
             tf = flops / (ms_kernel * 1e-3) / 1e12
             res["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -411,6 +419,7 @@ def main():
     _lib.launch_count(reset=True)
     ms = timed_region(step, args.steps, args.warmup, world, sampler)
     launches = _lib.launch_count() - args.warmup
+    per_rank_us = [round(1e3 * v / args.steps, 2) for v in LAST_PER_RANK_MS]
     clocks = sampler.finish() if sampler else None
     ms_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
@@ -449,7 +458,7 @@ def main():
                        "l2": "inputs larger than L2: two 512 MiB batches used alternately",
                        "search_workload": "1M x 2048 bf16 database row-sharded over the GPUs, top-100, 10k-query batch and 70 queries "
                                           "(configs[3]); strong scaling"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "per_rank_us_per_step": per_rank_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": TAIL_NCU_TRAFFIC,
                          "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth; "
