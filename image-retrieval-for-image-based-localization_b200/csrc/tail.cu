@@ -425,7 +425,28 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     stamp(P, 1);
     if (pool_only) return;
 
+    // phase-B setup (barriers, TMEM, tensor-map prefetch) does not depend on the pooled vectors: do it before the grid
+    // barrier instead of on the critical path behind it
+    const bool projecting = whiten && (int)blockIdx.x < P.units;
+    if (projecting) {
+        if (tid == 0) {
+            for (int s2 = 0; s2 < P.n_slots; ++s2) {
+                mbar_init(&fullB[s2], 1);
+                mbar_init(&emptyB[s2], 1);          // freed by tcgen05.commit
+            }
+            mbar_init(&accB, 1);
+            fence_barrier_init();
+            prefetch_tmap(&tmHi);
+            prefetch_tmap(&tmLo);
+        }
+        if (warp == 2) {
+            tmem_alloc(&tmem_slot, TAIL_NT);
+            tmem_relinquish();
+        }
+        tc_fence_before();
+    }
     grid.sync();
+    if (projecting) tc_fence_after();
     stamp(P, 2);
 
     // ------------------------------------------------------------------ no whitening
@@ -452,24 +473,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     // ------------------------------------------------------------------ phase B: split-K projection units
     if ((int)blockIdx.x < P.units) {
         constexpr uint32_t idesc = make_idesc_bf16(TAIL_MB, TAIL_NT);
-        if (tid == 0) {
-            for (int s2 = 0; s2 < P.n_slots; ++s2) {
-                mbar_init(&fullB[s2], 1);
-                mbar_init(&emptyB[s2], 1);          // freed by tcgen05.commit
-            }
-            mbar_init(&accB, 1);
-            fence_barrier_init();
-            prefetch_tmap(&tmHi);
-            prefetch_tmap(&tmLo);
-        }
-        if (warp == 2) {
-            tmem_alloc(&tmem_slot, TAIL_NT);
-            tmem_relinquish();
-        }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_slot;
+        const uint32_t tmem_acc = tmem_slot;       // allocated before the grid barrier
         int slot = 0;               // ring position of the producer / the MMA issuer (same tile sequence)
         uint32_t phase = 0;
         uint32_t acc_phase = 0;
@@ -592,11 +596,23 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
             float yreg[YR];
             const bool in_regs = P.D_out <= YR * TAIL_THREADS;
 #pragma unroll
-            for (int i = 0; i < YR; ++i) {
-                const int d = tid + i * TAIL_THREADS;
-                yreg[i] = 0.0f;
-                if (d < P.D_out)
-                    for (int ks = 0; ks < P.n_kslices; ++ks) yreg[i] += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
+            for (int i = 0; i < YR; ++i) yreg[i] = 0.0f;
+            // 4 slices x 8 dims = up to 32 independent L2 loads in flight per thread, added in slice order (an
+            // accumulate-as-you-load loop serialised 32 L2 latencies: ~6 us on the critical path)
+            for (int ks0 = 0; ks0 < P.n_kslices; ks0 += 4) {
+                float t[4][YR];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int i = 0; i < YR; ++i) {
+                        const int d = tid + i * TAIL_THREADS;
+                        t[u][i] = (ks0 + u < P.n_kslices && d < P.D_out)
+                                      ? __ldcg(P.part + ((size_t)(ks0 + u) * P.N + n) * P.D_out + d) : 0.0f;
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int i = 0; i < YR; ++i) yreg[i] += t[u][i];
             }
             // first L2N: ||g_n|| from the split pooled vector
             float sg = 0.0f;
