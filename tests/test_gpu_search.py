@@ -241,7 +241,7 @@ def test_bad_arguments_raise():
                         torch.zeros(10, 128, device=DEV, dtype=torch.bfloat16), 5)
 
 
-@pytest.mark.parametrize("Q", [70, 1000])
+@pytest.mark.parametrize("Q", [70, 1000, 10_000])
 def test_million_row_database_properties(Q):
     """BASELINE.json config 4 at full size (1M x 2048, top-100): too large for the CPU oracle in
     seconds, so check size-independent properties: sortedness, fp32-exact returned scores, planted

@@ -114,3 +114,21 @@ def test_rmac_region_grid_matches_fixture(golden):
     for (H, W, L) in sorted({tuple(r[:3]) for r in grid}):
         want = [tuple(r[3:]) for r in grid if tuple(r[:3]) == (H, W, L)]
         assert [(0, 0, H, W)] + LF.rmac_regions(H, W, L) == want, (H, W, L)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) must print ONE JSON line with the
+    contract keys, without a GPU.  One step of the oracle port of globalHead.forward on the full 64 x 2048 x 32 x 32 batch."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "descriptors/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config"):
+        assert key in line
