@@ -124,26 +124,48 @@ mine_filter_kernel(const int32_t* __restrict__ cand, int Q, int Kc, const int32_
     int taken_cluster[MINE_MAX_NNUM];
     int count = 0;
     const int qc = __ldg(q_cluster + q);
-    for (int r = 0; r < Kc && count < nnum; ++r) {
-        const int32_t j = __ldg(cand + (size_t)q * Kc + r);
-        if (j < 0 || j >= P) continue;
-        const int c = __ldg(pool_cluster + j);
-        bool clash = c == qc;
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(q32) | reinterpret_cast<uintptr_t>(pool32)) & 15) == 0;
+    // 32 candidates and their clusters are fetched at once (one lane each); the greedy walk itself then runs on
+    // registers -- the serial version paid two dependent memory latencies per candidate
+    for (int r0 = 0; r0 < Kc && count < nnum; r0 += 32) {
+        const int32_t jl = r0 + lane < Kc ? __ldg(cand + (size_t)q * Kc + r0 + lane) : -1;
+        const int cl = (jl >= 0 && jl < P) ? __ldg(pool_cluster + jl) : -1;
+        const int lim = min(32, Kc - r0);
+        for (int t = 0; t < lim && count < nnum; ++t) {
+            const int32_t j = __shfl_sync(0xffffffffu, jl, t);
+            const int c = __shfl_sync(0xffffffffu, cl, t);
+            if (j < 0 || j >= P) continue;
+            bool clash = c == qc;
 #pragma unroll 1
-        for (int t = 0; t < count; ++t) clash |= taken_cluster[t] == c;
-        if (clash) continue;
-        taken_cluster[count] = c;
-        if (lane == 0) out_sel[(size_t)q * nnum + count] = j;
-        if (q32 && pool32 && out_dist) {
-            float ss = 0.0f;
-            for (int d = lane; d < D; d += 32) {
-                const float df = __ldg(q32 + (size_t)q * D + d) - __ldg(pool32 + (size_t)j * D + d) + 1e-6f;
-                ss = fmaf(df, df, ss);
+            for (int u = 0; u < count; ++u) clash |= taken_cluster[u] == c;
+            if (clash) continue;
+            taken_cluster[count] = c;
+            if (lane == 0) out_sel[(size_t)q * nnum + count] = j;
+            if (q32 && pool32 && out_dist) {
+                const float* a = q32 + (size_t)q * D;
+                const float* b = pool32 + (size_t)j * D;
+                float ss = 0.0f;
+                if (vec) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                    for (int d = lane * 4; d < D; d += 128) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(a + d));
+                        const float4 y = __ldg(reinterpret_cast<const float4*>(b + d));
+                        const float d0 = x.x - y.x + 1e-6f, d1 = x.y - y.y + 1e-6f, d2 = x.z - y.z + 1e-6f, d3 = x.w - y.w + 1e-6f;
+                        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+                    }
+                    ss = (s0 + s1) + (s2 + s3);
+                } else {
+                    for (int d = lane; d < D; d += 32) {
+                        const float df = __ldg(a + d) - __ldg(b + d) + 1e-6f;
+                        ss = fmaf(df, df, ss);
+                    }
+                }
+                ss = warp_sum(ss);
+                if (lane == 0) out_dist[(size_t)q * nnum + count] = sqrtf(ss);
             }
-            ss = warp_sum(ss);
-            if (lane == 0) out_dist[(size_t)q * nnum + count] = sqrtf(ss);
+            ++count;
         }
-        ++count;
     }
     if (lane == 0) {
         out_count[q] = count;

@@ -130,7 +130,8 @@ __device__ __forceinline__ void compact_dispatch(unsigned long long* L, int n, i
 // ---------------------------------------------------------------------------------------
 // the search kernel
 // ---------------------------------------------------------------------------------------
-template <int MODE>
+// LABELS: the variant with label exclusion (mining) is a separate instantiation, so the plain search keeps its registers
+template <int MODE, bool LABELS>
 __global__ void __launch_bounds__(SEARCH_THREADS, 1)
 search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SearchParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -246,8 +247,8 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (MODE == MODE_TOPK) {
                 L = P.lists + ((size_t)s * P.Qpad + qg) * P.cap;
                 if (valid && P.tau0) tau = nextafterf(__ldg(P.tau0 + qg), -INFINITY);
-                if (valid && P.q_label) qlab = __ldg(P.q_label + qg);
             }
+            if (LABELS && MODE != MODE_DENSE && valid) qlab = __ldg(P.q_label + qg);
             for (int n = n0; n < n1; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
@@ -260,15 +261,15 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const int cb = col0 + c * 32;
                     if (MODE == MODE_TOPK) {
                         if (valid) {
-                            if (P.db_label || cb + 32 > P.N) {
-                                // mining (label exclusion) and the ragged last tile: checked path
+                            if (cb + 32 > P.N) {
+                                // the ragged last tile: checked path
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
                                     const float sc = __uint_as_float(v[j]);
                                     if (sc > tau) {
                                         const int idx = cb + j;
                                         bool ok = idx < P.N;
-                                        if (ok && P.db_label) ok = __ldg(P.db_label + idx) != qlab;
+                                        if (LABELS && ok) ok = __ldg(P.db_label + idx) != qlab;
                                         if (ok) L[cnt++] = ((unsigned long long)(uint32_t)idx << 32) | (unsigned long long)v[j];
                                     }
                                 }
@@ -277,22 +278,48 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                 // its full latency (measured: ~165 cycles per append, which put the epilogue on the MMA's
                                 // critical path).  Predicated store + predicated bump of a 32-bit byte offset instead.
                                 uint32_t off = (uint32_t)cnt * 8u;
+                                if (LABELS) {
+                                    // mining: candidates of the query's own cluster are skipped; the label is only loaded
+                                    // (predicated) for scores that beat the threshold
+                                    const int32_t* lab = P.db_label + cb;
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const uint32_t ix = (uint32_t)(cb + j);
-                                    asm volatile(
-                                        "{\n\t"
-                                        ".reg .pred p;\n\t"
-                                        ".reg .u64 a;\n\t"
-                                        "setp.gt.f32 p, %2, %3;\n\t"
-                                        "@p cvt.u64.u32 a, %0;\n\t"
-                                        "@p add.u64 a, a, %1;\n\t"
-                                        "@p st.global.v2.b32 [a], {%4, %5};\n\t"
-                                        "@p add.u32 %0, %0, 8;\n\t"
-                                        "}"
-                                        : "+r"(off)
-                                        : "l"(L), "f"(__uint_as_float(v[j])), "f"(tau), "r"(v[j]), "r"(ix)
-                                        : "memory");
+                                    for (int j = 0; j < 32; ++j) {
+                                        const uint32_t ix = (uint32_t)(cb + j);
+                                        asm volatile(
+                                            "{\n\t"
+                                            ".reg .pred p;\n\t"
+                                            ".reg .u64 a;\n\t"
+                                            ".reg .s32 l;\n\t"
+                                            "setp.gt.f32 p, %2, %3;\n\t"
+                                            "@p ld.global.nc.s32 l, [%6];\n\t"
+                                            "@p setp.ne.s32 p, l, %7;\n\t"
+                                            "@p cvt.u64.u32 a, %0;\n\t"
+                                            "@p add.u64 a, a, %1;\n\t"
+                                            "@p st.global.v2.b32 [a], {%4, %5};\n\t"
+                                            "@p add.u32 %0, %0, 8;\n\t"
+                                            "}"
+                                            : "+r"(off)
+                                            : "l"(L), "f"(__uint_as_float(v[j])), "f"(tau), "r"(v[j]), "r"(ix), "l"(lab + j), "r"(qlab)
+                                            : "memory");
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const uint32_t ix = (uint32_t)(cb + j);
+                                        asm volatile(
+                                            "{\n\t"
+                                            ".reg .pred p;\n\t"
+                                            ".reg .u64 a;\n\t"
+                                            "setp.gt.f32 p, %2, %3;\n\t"
+                                            "@p cvt.u64.u32 a, %0;\n\t"
+                                            "@p add.u64 a, a, %1;\n\t"
+                                            "@p st.global.v2.b32 [a], {%4, %5};\n\t"
+                                            "@p add.u32 %0, %0, 8;\n\t"
+                                            "}"
+                                            : "+r"(off)
+                                            : "l"(L), "f"(__uint_as_float(v[j])), "f"(tau), "r"(v[j]), "r"(ix)
+                                            : "memory");
+                                    }
                                 }
                                 cnt = (int)(off >> 3);
                             }
@@ -318,6 +345,11 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         // Each maximum is the score of a distinct row, so the k-th largest of them is a lower bound of the
                         // query's k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.
                         if (valid) {
+                            if (LABELS) {                   // mining: rows of the query's own cluster do not count
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (__ldg(P.db_label + cb + j) == qlab) v[j] = 0xff800000u;      // -inf
+                            }
                             float m[32 / GROUP];
 #pragma unroll
                             for (int g = 0; g < 32 / GROUP; ++g) {
@@ -443,18 +475,24 @@ static int launch_search(int mode, const void* q, int Q, const void* db, long lo
     P.b_policy = plan.mt == 1 ? 1 : 0;
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_DENSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_GROUPMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_GROUPMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_dev = dev.device;
     }
     const int grid = plan.units < dev.num_sms ? plan.units : dev.num_sms;
-    if (mode == MODE_TOPK)
-        search_kernel<MODE_TOPK><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
-    else if (mode == MODE_GROUPMAX)
-        search_kernel<MODE_GROUPMAX><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
-    else
-        search_kernel<MODE_DENSE><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+    const bool labels = P.db_label != nullptr;
+    if (mode == MODE_TOPK) {
+        if (labels) search_kernel<MODE_TOPK, true><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+        else search_kernel<MODE_TOPK, false><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+    } else if (mode == MODE_GROUPMAX) {
+        if (labels) search_kernel<MODE_GROUPMAX, true><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+        else search_kernel<MODE_GROUPMAX, false><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+    } else {
+        search_kernel<MODE_DENSE, false><<<grid, SEARCH_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+    }
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;
@@ -478,19 +516,24 @@ using namespace cir;
 // database rows is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
 // and most appends (measured 53.6 ms -> 30.9 ms on 10k x 1M with an exact tau0).
 static int sample_rows(int Q, long long N, int k) {
-    // ~N/32 rows (3 % extra scan), a power of two in [2048, 32768]; small databases skip the pre-pass.
-    // 10k x 1M: n0 = 32768 -> 33.8 ms, 16384 -> 34.7 ms, exact 32.5 ms.
-    if (N < 65536) return 0;
+    // Large databases: ~N/32 rows (3 % extra scan), a power of two in [2048, 32768], with at least 4 k groups of 8 rows so
+    // that the k-th largest group maximum stays a tight bound (10k x 1M: n0 = 32768 -> 32.3 ms; an exact threshold: 31.5 ms).
+    // Mid-size databases (8,192 .. 65,535 rows, more than one query tile: mining, 2,000 x 20,000): 2 k groups (>= 1024
+    // rows, <= N / 4) -- without a threshold every (split, query) list starts by taking every score and compacting
+    // every ~400 appends, which cost more than the whole GEMM.  Small or single-tile problems skip the pre-pass.
+    if (N < 8192 || (Q <= SEARCH_BM && N < 65536)) return 0;
     static const char* dbg = getenv("CIR_DEBUG_SAMPLE_ROWS");        // experiments only
     int n0 = 2048;
-    if (dbg && atoi(dbg) >= 2048) {
+    if (dbg && atoi(dbg) >= 1024 && atoi(dbg) <= SAMPLE_MAX_ROWS) {
         n0 = atoi(dbg) / 256 * 256;
-        if (n0 >= N) n0 = 2048;
-    } else {
+        if ((long long)n0 * 2 > N) n0 = 1024;
+    } else if (N >= 65536) {
         while (n0 * 2 <= SAMPLE_MAX_ROWS && (long long)n0 * 2 * 32 <= N + N / 2) n0 *= 2;
+        while (k > n0 / GROUP / 4 && n0 * 2 <= SAMPLE_MAX_ROWS && (long long)n0 * 2 * 4 <= N) n0 *= 2;
+    } else {
+        n0 = 1024;
+        while (k > n0 / GROUP / 2 && (long long)n0 * 2 * 4 <= N) n0 *= 2;
     }
-    // the k-th largest of n0 / 8 group maxima must stay a tight bound: at least 4 k groups when the database allows
-    while (k > n0 / GROUP / 4 && n0 * 2 <= SAMPLE_MAX_ROWS && (long long)n0 * 2 * 4 <= N) n0 *= 2;
     if (k > n0 / GROUP / 2) return 0;
     return n0;
 }
@@ -559,7 +602,7 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
     const int n0_ws = sample_rows(Q, N, k);
     const SearchWs w = search_ws_layout(plan, Q, search_cap_for_k(k), n0_ws);
     char* ws = static_cast<char*>(workspace);
-    const int n0 = (tau0 || q_label || (flags & CIR_SEARCH_NO_PREPASS)) ? 0 : n0_ws;
+    const int n0 = (tau0 || (flags & CIR_SEARCH_NO_PREPASS)) ? 0 : n0_ws;
     if (n0 > 0) {
         // pre-pass: maxima of every 8 consecutive rows of the first n0 rows, then the k-th largest of them per query
         float* dense = reinterpret_cast<float*>(ws + w.dense);
@@ -567,6 +610,8 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
         SearchParams D{};
         D.dense_out = dense;
         D.dense_ld = n0 / GROUP;
+        D.q_label = q_label;          // mining: the threshold only counts rows the query may take
+        D.db_label = db_label;
         rc = launch_search(MODE_GROUPMAX, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
                            static_cast<cudaStream_t>(stream));
         if (rc) return rc;

@@ -162,3 +162,31 @@ if what == "regions":
         ]:
             ms = timeit(fn)
             print(f"regions {name:36s} {ms*1e3:8.1f} us  {gb/ms:8.1f} GB/s(x only)")
+if what == "mining":
+    from torch.profiler import profile, ProfilerActivity
+    from cirtorch_b200.mining import mine_hard_negatives_rows
+    g = torch.Generator(device=dev).manual_seed(0)
+    def unit(n, d):
+        x = torch.randn((n, d), device=dev, generator=g); return x / x.norm(dim=1, keepdim=True)
+    centres = unit(700, 2048)
+    pc = torch.randint(0, 700, (20000,), device=dev, generator=g); qc = torch.randint(0, 700, (2000,), device=dev, generator=g)
+    pool = centres[pc] * 0.6 + unit(20000, 2048); pool = (pool / pool.norm(dim=1, keepdim=True)).contiguous()
+    q = centres[qc] * 0.6 + unit(2000, 2048); q = (q / q.norm(dim=1, keepdim=True)).contiguous()
+    for _ in range(3): mine_hard_negatives_rows(q, pool, qc.int(), pc.int(), 5)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5): mine_hard_negatives_rows(q, pool, qc.int(), pc.int(), 5)
+        torch.cuda.synchronize()
+    for e in prof.key_averages():
+        if e.device_time_total > 0:
+            print(f"mining: {e.key[:80]:80s} x{e.count:3d}  {e.device_time_total / e.count:10.1f} us")
+    print("mining total per call: %.1f us" % (timeit(lambda: mine_hard_negatives_rows(q, pool, qc.int(), pc.int(), 5), n=10) * 1e3))
+if what == "midsize":
+    D = 2048
+    for (Q, N, mode) in ((2000, 20000, "bf16"), (2000, 20000, "bf16x3"), (5000, 50000, "bf16"), (1000, 10000, "bf16")):
+        x = torch.randn((N, D), device=dev); x = x / x.norm(dim=1, keepdim=True)
+        q = torch.randn((Q, D), device=dev); q = q / q.norm(dim=1, keepdim=True)
+        dbp = S.pack_rows(x, "db", mode); qp = S.pack_rows(q, "query", mode)
+        ms = timeit(lambda: S.search_packed(qp, dbp, 100), n=10)
+        Kd = dbp.shape[1]
+        print(f"midsize Q={Q} N={N} {mode}: {ms*1e3:8.1f} us  {2*Q*N*Kd/ms/1e9:7.1f} TF  sample={os.environ.get('CIR_DEBUG_SAMPLE_ROWS','rule')}")

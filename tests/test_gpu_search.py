@@ -195,6 +195,27 @@ def test_equal_scores_flood_large_batch():
     np.testing.assert_array_equal(i.cpu().numpy(), np.tile(np.arange(100, dtype=np.int32), (600, 1)))
 
 
+@pytest.mark.parametrize("Q,N,D,k", [(300, 20_000, 128, 80), (200, 9_000, 64, 10), (640, 40_000, 64, 100)])
+def test_mid_size_database_threshold_prepass(Q, N, D, k):
+    """8,192 <= N < 65,536 with several query tiles runs the group-max threshold pre-pass (2 k groups of 8 rows); with
+    labels (mining) the threshold only counts rows outside the query's cluster.  Lists == oracle, with and without labels."""
+    from cirtorch_b200 import search as S
+    db, db_lab = clustered_unit_rows(N, D, 200, 0.9, seed=31)
+    q, q_lab = clustered_unit_rows(Q, D, 200, 0.9, seed=31)
+    ex = _exact(q, db)
+    qp, dbp = S.pack_rows(_dev(q), "query", "bf16x3"), S.pack_rows(_dev(db), "db", "bf16x3")
+    s, i = S.search_packed(qp, dbp, k)
+    check_topk_against_exact(i.cpu().numpy(), s.cpu().numpy(), ex, k, TOL_X3)
+    ql = torch.from_numpy(q_lab.astype(np.int32)).to(DEV)
+    dl = torch.from_numpy(db_lab.astype(np.int32)).to(DEV)
+    s2, i2 = S.search_packed(qp, dbp, k, q_label=ql, db_label=dl)
+    ex_masked = ex.copy()
+    ex_masked[q_lab[:, None] == db_lab[None, :]] = -np.inf          # the query's own cluster is not a candidate
+    i2n = i2.cpu().numpy()
+    assert not (db_lab[i2n] == q_lab[:, None]).any()
+    check_topk_against_exact(i2n, s2.cpu().numpy(), ex_masked, k, TOL_X3)
+
+
 def test_equal_scores_flood():
     """All database rows identical: every score ties; the lowest indices must win."""
     from cirtorch_b200 import search as S
