@@ -64,3 +64,40 @@ print(json.dumps({"config": "alpha-QE k=10 alpha=3, 10k queries x 1M x 2048, the
 ms_dba = timeit(lambda: rerank.dba_rows(db, k=10, alpha=3.0, index=index, row_begin=0, row_end=20_000, chunk=10_000), n=2, warm=1)
 print(json.dumps({"config": "DBA k=10 alpha=3 over 1M x 2048: 20,000-row slice (2 x 10k-query searches + aggregation)", "gpu_ms": ms_dba,
                   "rows_per_s": 20_000 / (ms_dba * 1e-3), "full_1M_pass_s_extrapolated": ms_dba * 50 / 1e3}))
+del db, index, q
+torch.cuda.empty_cache()
+
+# ---- config 1: ResNet50-GeM extract_vectors + exhaustive search, rOxford5k shape (70 queries vs 4,993 database images),
+# synthetic 1024 px images, random-init weights.  The torchvision backbone is stock PyTorch (not part of the product);
+# a 32-image sample is timed and scaled to the 5,063 images of the set.
+from cirtorch_b200.extract import resnet50_gem, extract_vectors
+net = resnet50_gem().to(dev).eval()
+imgs = torch.randn((32, 3, 1024, 1024), generator=torch.Generator().manual_seed(0))
+t_sample = None
+for rep in range(2):            # first pass = cuDNN autotune / warm-up
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    vecs = extract_vectors(net, imgs, image_size=1024, transform=None, batch_size=8, device=dev)
+    torch.cuda.synchronize(); t_sample = time.perf_counter() - t0
+fm = torch.relu(torch.randn((8, 2048, 32, 32), device=dev))
+with torch.no_grad():
+    ms_tail8 = timeit(lambda: net.ret_head(fm), n=20)
+dbv = unit(4993, 2048, g); qv = unit(70, 2048, g)
+ms_rank = timeit(lambda: S.rank(dbv.t(), qv.t()), n=5)                      # full N x Q ranking like np.argsort(-scores, axis=0)
+ms_topk = timeit(lambda: S.search_topk(qv.t(), dbv.t(), 100), n=10)
+# the reference's CPU path on the same host, 2 images (torchvision backbone + oracle head), then np.dot + np.argsort
+sys.path.insert(0, ROOT)
+from oracle import cirtorch_oracle as O
+net_cpu = resnet50_gem().eval()
+with torch.no_grad():
+    t0 = time.perf_counter()
+    f = net_cpu.body(imgs[:2])
+    O.head_forward(f, 3.0, 1e-6, net_cpu.ret_head.whiten.weight, net_cpu.ret_head.whiten.bias)
+    cpu_img_s = (time.perf_counter() - t0) / 2
+t0 = time.perf_counter(); O.rank(dbv.t().cpu().numpy(), qv.t().cpu().numpy()); cpu_rank_s = time.perf_counter() - t0
+print(json.dumps({"config": "ResNet50-GeM extract_vectors + exhaustive search, 70 q vs 4,993 db, 1024 px (BASELINE configs[0])",
+                  "gpu_images_per_s": 32 / t_sample, "gpu_extract_5063_images_s_extrapolated": 5063 * t_sample / 32,
+                  "gpu_tail_ms_per_8_images": ms_tail8, "gpu_full_ranking_ms": ms_rank, "gpu_top100_ms": ms_topk,
+                  "cpu_reference_s_per_image": cpu_img_s, "cpu_extract_5063_images_s_extrapolated": 5063 * cpu_img_s,
+                  "cpu_rank_s": cpu_rank_s, "cpu_threads": torch.get_num_threads(),
+                  "note": "backbone = stock torchvision fp32 (excluded from the roofline); sample of 32 images (GPU) / 2 images (CPU) "
+                          "scaled linearly; includes the H2D copy of the images and the D2H copy of the descriptors"}))
