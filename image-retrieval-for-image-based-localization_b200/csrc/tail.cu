@@ -302,6 +302,11 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     const bool whiten = !pool_only && !(P.flags & CIR_TAIL_NO_WHITEN);
 
     stamp(P, 0);
+    if (P.stamps && threadIdx.x == 0) {          // profiling aid: which SM ran this CTA
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.stamps[(size_t)blockIdx.x * 8 + 7] = smid;
+    }
     int conv_unit = -1;                      // which projection unit's W tile currently sits in Bt
     const bool own_unit = whiten && (int)blockIdx.x < P.units;
 

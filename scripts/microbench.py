@@ -190,3 +190,37 @@ if what == "midsize":
         ms = timeit(lambda: S.search_packed(qp, dbp, 100), n=10)
         Kd = dbp.shape[1]
         print(f"midsize Q={Q} N={N} {mode}: {ms*1e3:8.1f} us  {2*Q*N*Kd/ms/1e9:7.1f} TF  sample={os.environ.get('CIR_DEBUG_SAMPLE_ROWS','rule')}")
+if what == "smid":
+    # is the phase-A straggler pattern tied to the SM?  per-CTA end of phase A over several launches + the SM id
+    import ctypes as C
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    B, Cc, H, W = 64, 2048, 32, 32
+    xs = [torch.relu(torch.randn((B, Cc, H, W), device=dev)) for _ in range(2)]
+    Wt = torch.randn(2048, 2048, device=dev) * 0.01
+    b = torch.zeros(2048, device=dev); p3 = torch.full((1,), 3.0, device=dev)
+    out = torch.empty((B, 2048), device=dev)
+    need = C.c_size_t(0); lib.cir_tail_workspace_bytes(B, Cc, 2048, C.byref(need))
+    ws = torch.zeros(need.value, dtype=torch.uint8, device=dev)
+    runs = []
+    for it in range(8):
+        x = xs[it & 1]
+        rc = lib.cir_tail_fwd(_lib.ptr(x), B, Cc, H, W, _lib.ptr(p3), 0, 1e-6, 1e-6, 0, _lib.ptr(Wt), _lib.ptr(b), 2048,
+                              _lib.ptr(out), 2048, _lib.ptr(ws), ws.numel(), 0x80000000, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :8].cpu().double()
+        runs.append(st)
+    import numpy as np
+    durA = np.stack([(r[:, 1] - r[:, 0]).numpy() / 1e3 for r in runs[2:]])       # [runs, cta] us
+    smid = np.stack([r[:, 7].numpy() for r in runs[2:]])
+    print("smid: cta->sm mapping identical across launches:", bool((smid == smid[0]).all()))
+    print("smid: per-launch mean %s  max %s" % (np.round(durA.mean(1), 1), np.round(durA.max(1), 1)))
+    m = durA.mean(0)
+    order = np.argsort(-m)
+    print("smid: slowest CTAs (cta, sm, mean us, std):", [(int(c), int(smid[0][c]), round(float(m[c]), 1), round(float(durA[:, c].std()), 2)) for c in order[:12]])
+    print("smid: fastest CTAs:", [(int(c), int(smid[0][c]), round(float(m[c]), 1)) for c in order[-8:]])
+    print("smid: corr between launches of per-CTA duration:", np.round(np.corrcoef(durA)[0, 1:], 2))
+    bysm = {}
+    for c in range(148): bysm.setdefault(int(smid[0][c]) // 2 // 9, []).append(m[c])
+    print("smid: mean by group of 18 SMs:", {k: round(float(np.mean(v)), 1) for k, v in sorted(bysm.items())})
