@@ -25,6 +25,8 @@ elif what in ("search10k", "search70"):
     from cirtorch_b200 import search as S
     N, D = 1_000_000, 2048
     Q = 10_000 if what == "search10k" else 70
+    if os.environ.get("CIR_PROFILE_Q"):
+        Q = int(os.environ["CIR_PROFILE_Q"])
     dbp = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
     for a in range(0, N, 125_000):
         blk = torch.randn((125_000, D), device=dev)

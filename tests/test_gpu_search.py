@@ -310,3 +310,21 @@ def test_index_save_load_roundtrip(tmp_path):
     index2 = store.load_index(str(tmp_path / "shard.pt"), device=DEV)
     s1, i1 = index2.search_rows(_dev(q), 10)
     assert torch.equal(i0, i1) and torch.equal(s0, s1) and int(i1.min()) >= 1000
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel():
+    """The experimental cta_group::2 variant of the search (CIR_SEARCH_2CTA=1, read once per process) must return
+    bit-identical lists; two subprocesses of scripts/pair_check.py, one per kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "scripts", "pair_check.py")
+    env = dict(os.environ)
+    env.pop("CIR_SEARCH_2CTA", None)
+    r = subprocess.run([sys.executable, script, "ref"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    env["CIR_SEARCH_2CTA"] = "1"
+    r = subprocess.run([sys.executable, script, "cmp"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert r.stdout.count("idx equal True scores equal True") == 4, r.stdout
