@@ -32,15 +32,23 @@ class ImageRetrievalNet(nn.Module):
         return F.interpolate(img, scale_factor=s, mode="bilinear", align_corners=False)   # GF_net.py:20-40
 
     def forward(self, img, scales=(1,), do_whitening=True):
-        descs = []
+        fused_sum = not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
+        acc, descs = None, []
         for s in scales:
             fmap = self.body(self._rescale(img, s))
             if isinstance(fmap, dict):          # the reference body returns {"mod1".."mod5"} (GF_algo.py:54-55)
                 fmap = fmap["mod5"]
-            descs.append(self.ret_head(fmap, do_whitening=do_whitening))
-        if len(descs) == 1:
-            return descs[0]
-        return torch.stack(descs, 0).mean(0)
+            if not fused_sum:
+                descs.append(self.ret_head(fmap, do_whitening=do_whitening))
+            elif acc is None:
+                acc = self.ret_head(fmap, do_whitening=do_whitening)
+            else:                               # later scales are added in the tail kernel's last phase
+                self.ret_head(fmap, do_whitening=do_whitening, out=acc, accumulate=True)
+        if not fused_sum:
+            return descs[0] if len(descs) == 1 else torch.stack(descs, 0).mean(0)
+        if len(scales) > 1:
+            acc.mul_(1.0 / len(scales))         # avg_pool1d over the scales, no re-normalisation (GF_net.py:84-85)
+        return acc
 
 
 def resnet50_gem(dim=2048, p=3.0, pretrained=False):

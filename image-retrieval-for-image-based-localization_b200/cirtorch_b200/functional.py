@@ -7,7 +7,8 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC, CIR_TAIL_NO_WHITEN, CIR_TAIL_POOL_ONLY
+from ._lib import (CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC, CIR_TAIL_ACCUMULATE, CIR_TAIL_NO_WHITEN,
+                   CIR_TAIL_POOL_ONLY)
 
 _POOL = {"GeM": CIR_POOL_GEM, "GeMmp": CIR_POOL_GEM, "MAC": CIR_POOL_MAC, "SPoC": CIR_POOL_SPOC}
 
@@ -21,7 +22,7 @@ def _as_f32_contig(x: torch.Tensor) -> torch.Tensor:
 _tail_ws_bytes = {}
 
 
-def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6):
+def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None):
     """One cooperative launch of the fused tail.  Returns the physical [N, D] buffer.
 
     Kept lean on the host (a launch is ~0.1 ms of GPU time): no detach / reshape copies, one stream query."""
@@ -33,7 +34,12 @@ def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6):
     N, Cc, H, W = x.shape
     whiten = not (flags & (CIR_TAIL_NO_WHITEN | CIR_TAIL_POOL_ONLY))
     D = weight.shape[0] if whiten else Cc
-    out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+    if out is None:
+        if flags & CIR_TAIL_ACCUMULATE:
+            raise ValueError("accumulate=True needs the buffer to add to (out=...)")
+        out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+    elif (tuple(out.shape) != (N, D) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device):
+        raise ValueError("out must be a contiguous fp32 %d x %d tensor on %s" % (N, D, x.device))
     if N == 0:
         return out
     p_stride = 0
@@ -192,14 +198,20 @@ class _TailFn(torch.autograd.Function):
 
 
 def descriptor_tail(x, p=None, eps=1e-6, weight=None, bias=None, pooling="GeM", do_whitening=True,
-                    pool_only=False, l2_eps=1e-6):
+                    pool_only=False, l2_eps=1e-6, out=None, accumulate=False):
     """pool -> L2N -> (whiten -> L2N).  Returns the physical N x D buffer (row = descriptor).
 
     globalHead.forward (cirtorch/modules/heads/global_head.py:52-67) returns its transpose view.
+    ``out``: write into this N x D buffer; with ``accumulate`` the descriptors are ADDED to it in the kernel's last phase
+    (the sum over scales of the fork's multi-scale mean, GF_net.py:74-92) -- inference only.
     """
     if pooling not in _POOL:
         raise KeyError(pooling)
     flags = CIR_TAIL_POOL_ONLY if pool_only else (0 if do_whitening else CIR_TAIL_NO_WHITEN)
+    if accumulate:
+        if pool_only:
+            raise ValueError("accumulate applies to descriptors, not to pool_only")
+        flags |= CIR_TAIL_ACCUMULATE
     if pooling in ("GeM", "GeMmp"):
         if p is None:
             raise ValueError("GeM pooling needs the exponent p")
@@ -210,9 +222,11 @@ def descriptor_tail(x, p=None, eps=1e-6, weight=None, bias=None, pooling="GeM", 
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and torch.is_tensor(t) and t.requires_grad for t in (x, p, weight, bias))
     if needs_grad:
+        if out is not None:
+            raise ValueError("out= / accumulate= are inference-only (no autograd through an in-place sum)")
         return _TailFn.apply(x, p, weight if do_whitening and not pool_only else None,
                              bias if do_whitening and not pool_only else None, eps, pooling, flags, l2_eps)
-    return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
+    return _tail_launch(x, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, out=out)
 
 
 def rmac_grid(H, W, L=3):

@@ -33,11 +33,20 @@ class globalHead(nn.Module):
             if hasattr(mod, "bias") and mod.bias is not None:
                 nn.init.constant_(mod.bias, 0.)
 
-    def forward(self, x, do_whitening=True):
-        y = LF.descriptor_tail(
-            x, p=getattr(self.pool, "p", None), eps=getattr(self.pool, "eps", 1e-6),
-            weight=self.whiten.weight, bias=self.whiten.bias, pooling=self.pool_name,
-            do_whitening=do_whitening, l2_eps=self.norm.eps)
+    def forward(self, x, do_whitening=True, out=None, accumulate=False):
+        """``out`` / ``accumulate`` (extensions, inference only): write the descriptors into / add them to an existing
+        D x N result of this head -- the running sum of the multi-scale mean (GF_net.py:74-92)."""
+        phys = None if out is None else out.permute(1, 0)          # the physical N x D buffer behind a D x N result
+        kw = dict(weight=self.whiten.weight, bias=self.whiten.bias, do_whitening=do_whitening, l2_eps=self.norm.eps,
+                  out=phys, accumulate=accumulate)
+        if self.pool_name in ("GeM", "GeMmp", "MAC", "SPoC"):
+            y = LF.descriptor_tail(x, p=getattr(self.pool, "p", None), eps=getattr(self.pool, "eps", 1e-6),
+                                   pooling=self.pool_name, **kw)
+        else:
+            # any other registered pooling (RMAC, ...): its own kernel(s), then L2N -> whiten -> L2N fused on the pooled
+            # N x C x 1 x 1 vectors (the mean of one value is the value)
+            v = self.pool(x)
+            y = LF.descriptor_tail(v.reshape(v.shape[0], v.shape[1], 1, 1), pooling="SPoC", **kw)
         return y.permute(1, 0)
 
 

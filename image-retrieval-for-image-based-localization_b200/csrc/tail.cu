@@ -300,6 +300,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     const int warp = tid >> 5;
     const bool pool_only = (P.flags & CIR_TAIL_POOL_ONLY) != 0;
     const bool whiten = !pool_only && !(P.flags & CIR_TAIL_NO_WHITEN);
+    const bool accumulate = (P.flags & CIR_TAIL_ACCUMULATE) != 0;     // out += descriptor (multi-scale sum, GF_net.py:74-92)
 
     stamp(P, 0);
     if (P.stamps && threadIdx.x == 0) {          // profiling aid: which SM ran this CTA
@@ -469,8 +470,11 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
 #pragma unroll
             for (int w = 0; w < TAIL_WARPS; ++w) tot += redn[w];
             const float denom = sqrtf(tot) + P.eps_l2;
-            for (int c = tid; c < P.C; c += TAIL_THREADS)
-                P.out[(size_t)n * P.out_ld + c] = __ldcg(g + c) / denom;
+            for (int c = tid; c < P.C; c += TAIL_THREADS) {
+                float* o = P.out + (size_t)n * P.out_ld + c;
+                const float y = __ldcg(g + c) / denom;
+                *o = accumulate ? *o + y : y;
+            }
         }
         return;
     }
@@ -644,13 +648,19 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
 #pragma unroll
             for (int i = 0; i < YR; ++i) {
                 const int d = tid + i * TAIL_THREADS;
-                if (d < P.D_out) P.out[(size_t)n * P.out_ld + d] = yreg[i] / denom;
+                if (d < P.D_out) {
+                    float* o = P.out + (size_t)n * P.out_ld + d;
+                    const float y = yreg[i] / denom;
+                    *o = accumulate ? *o + y : y;
+                }
             }
             if (!in_regs) {
                 for (int d = tid + YR * TAIL_THREADS; d < P.D_out; d += TAIL_THREADS) {
                     float acc = 0.0f;
                     for (int ks = 0; ks < P.n_kslices; ++ks) acc += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
-                    P.out[(size_t)n * P.out_ld + d] = (acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f)) / denom;
+                    float* o = P.out + (size_t)n * P.out_ld + d;
+                    const float y = (acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f)) / denom;
+                    *o = accumulate ? *o + y : y;
                 }
             }
         }
@@ -699,6 +709,8 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     CIR_REQUIRE(p_stride == 0 || p_stride == 1, CIR_ERR_INVALID_ARG, "cir_tail_fwd: p_stride must be 0 or 1");
     const bool pool_only = flags & CIR_TAIL_POOL_ONLY;
     const bool whiten = !pool_only && !(flags & CIR_TAIL_NO_WHITEN);
+    CIR_REQUIRE(!(pool_only && (flags & CIR_TAIL_ACCUMULATE)), CIR_ERR_INVALID_ARG,
+                "cir_tail_fwd: CIR_TAIL_ACCUMULATE applies to descriptors, not to CIR_TAIL_POOL_ONLY");
     if (!whiten) D_out = C;
     CIR_REQUIRE(out_ld >= D_out, CIR_ERR_INVALID_ARG, "cir_tail_fwd: out_ld %d < D_out %d", out_ld, D_out);
     const DeviceInfo& dev = device_info();

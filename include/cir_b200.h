@@ -43,6 +43,8 @@ extern "C" {
 /* flags of cir_tail_fwd */
 #define CIR_TAIL_NO_WHITEN 1u   /* globalHead.forward(x, do_whitening=False)            */
 #define CIR_TAIL_POOL_ONLY 2u   /* stop after pooling: GeM.forward alone (no L2N)       */
+#define CIR_TAIL_ACCUMULATE 4u  /* out += descriptor instead of out = descriptor: the sum over scales of the multi-scale
+                                   mean, ImageRetrievalNet.forward cirtorch/models/GF_net.py:74-92 (divide by S afterwards) */
 #define CIR_TAIL_DEBUG_STAMPS 0x80000000u /* profiling aid: every CTA writes %globaltimer at its phase
                                    boundaries into the last 64 KB of the workspace ([cta][8] u64) */
 

@@ -17,7 +17,7 @@ def _rel(a, b, dim=0):
 
 def _head(dim, pooling="GeM", p=3.0):
     from cirtorch_b200.modules.heads.global_head import globalHead
-    params = {"p": p, "eps": 1e-6} if pooling in ("GeM", "GeMmp") else {}
+    params = {"p": p, "eps": 1e-6} if pooling in ("GeM", "GeMmp") else ({"L": 3} if pooling == "RMAC" else {})
     return globalHead(pooling={"name": pooling, "params": params}, normal={"name": "L2N", "params": {}}, dim=dim)
 
 
@@ -152,6 +152,62 @@ def test_regional_pooling_vs_oracle_layer4_shape():
         assert _rel(out2.cpu().reshape(shape[0], C).t(), ref2.reshape(shape[0], C).t()) < RTOL
     with pytest.raises(ValueError):
         LF.region_pool(torch.zeros(1, 4, 8, 8, device=DEV), [(0, 0, 9, 8)], pooling="MAC")
+
+
+def test_accumulate_flag_and_multiscale_sum(golden):
+    """CIR_TAIL_ACCUMULATE: descriptors added in the kernel's last phase == the fork's multi-scale mean (GF_net.py:74-92,
+    fixture produced by the reference's avg_pool1d), for whitened and un-whitened heads; inference only."""
+    from cirtorch_b200.extract import ImageRetrievalNet
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(5)
+    for do_whitening in (True, False):
+        head = _head(96).to(DEV).eval()
+        xs = [torch.relu(torch.randn(5, 96, h, w)) for (h, w) in ((8, 8), (6, 5), (11, 7))]
+        refs = [O.head_forward(x, 3.0, 1e-6, head.whiten.weight.detach().cpu(), head.whiten.bias.detach().cpu(),
+                               do_whitening=do_whitening) for x in xs]
+        want = O.multiscale_mean(refs)
+        with torch.no_grad():
+            acc = head(xs[0].to(DEV), do_whitening=do_whitening)
+            for x in xs[1:]:
+                ret = head(x.to(DEV), do_whitening=do_whitening, out=acc, accumulate=True)
+                assert ret.data_ptr() == acc.data_ptr()
+            acc.mul_(1.0 / len(xs))
+        assert _rel(acc.cpu(), want) < RTOL
+    g = golden("multiscale")           # [S, D, N] per-scale descriptors -> [D, N] from the reference
+    np.testing.assert_allclose(O.multiscale_mean([torch.from_numpy(p_) for p_ in g["preds"]]).numpy(), g["out"], rtol=1e-6)
+
+    class Body(torch.nn.Module):       # a stand-in backbone: fixed 1x1 conv + ReLU, output follows the image size
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 96, 1)
+
+        def forward(self, img):
+            return {"mod5": torch.relu(self.conv(img))}
+
+    net = ImageRetrievalNet(Body(), _head(96)).to(DEV).eval()
+    img = torch.randn(4, 3, 32, 24, device=DEV)
+    scales = (1, 0.5, 2 ** -0.5)
+    with torch.no_grad():
+        got = net(img, scales=scales)
+        per_scale = [net.ret_head(net.body(net._rescale(img, s))["mod5"]).clone() for s in scales]
+    want = torch.stack(per_scale, 0).mean(0)
+    assert _rel(got.cpu(), want.cpu()) < 1e-6
+    assert float(got.norm(dim=0).max()) <= 1.0 + 1e-5
+    with pytest.raises(ValueError):
+        LF.descriptor_tail(torch.zeros(2, 8, 4, 4, device=DEV), p=3.0, do_whitening=False, accumulate=True)
+
+
+def test_global_head_with_rmac_pooling():
+    """Any registered pooling goes through globalHead: RMAC (its own one-pass kernel) -> fused L2N / whiten / L2N."""
+    torch.manual_seed(6)
+    x = torch.relu(torch.randn(3, 64, 12, 10))
+    head = _head(64, pooling="RMAC").to(DEV).eval()
+    with torch.no_grad():
+        got = head(x.to(DEV))
+    v = O.rmac_forward(x, L=3)
+    want = O.l2n(torch.nn.functional.linear(O.l2n(v.reshape(3, 64)), head.whiten.weight.detach().cpu(), head.whiten.bias.detach().cpu()))
+    assert got.shape == (64, 3)
+    assert _rel(got.cpu(), want.t()) < RTOL
 
 
 def test_state_dict_keys_and_empty_batch():
