@@ -33,7 +33,7 @@ class globalHead(nn.Module):
             if hasattr(mod, "bias") and mod.bias is not None:
                 nn.init.constant_(mod.bias, 0.)
 
-    def forward(self, x, do_whitening=True, out=None, accumulate=False):
+    def forward(self, x, do_whitening=True, *, out=None, accumulate=False):
         """``out`` / ``accumulate`` (extensions, inference only): write the descriptors into / add them to an existing
         D x N result of this head -- the running sum of the multi-scale mean (GF_net.py:74-92)."""
         phys = None if out is None else out.permute(1, 0)          # the physical N x D buffer behind a D x N result

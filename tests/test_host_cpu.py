@@ -63,7 +63,14 @@ def test_registries_and_signatures_mirror_reference():
     assert list(inspect.signature(GeM.__init__).parameters)[1:] == ["p", "eps"]
     assert list(inspect.signature(GeMmp.__init__).parameters)[1:] == ["p", "mp", "eps"]
     assert list(inspect.signature(globalHead.__init__).parameters)[1:] == ["pooling", "normal", "dim", "norm_act"]
-    assert list(inspect.signature(globalHead.forward).parameters)[1:] == ["x", "do_whitening"]
+    fwd = inspect.signature(globalHead.forward).parameters
+    positional = [n for n, a in fwd.items() if a.kind == a.POSITIONAL_OR_KEYWORD][1:]
+    assert positional == ["x", "do_whitening"]                      # the reference's call signature
+    assert all(a.default is not a.empty for n, a in fwd.items() if a.kind == a.KEYWORD_ONLY)   # extensions are optional
+    from cirtorch_b200.modules.pools import RMAC, Rpool
+    assert POOLING_LAYERS["RMAC"] is RMAC and POOLING_LAYERS["ROIpool"] is Rpool
+    assert list(inspect.signature(RMAC.__init__).parameters)[1:] == ["L", "eps"]
+    assert list(inspect.signature(Rpool.__init__).parameters)[1:] == ["rpool", "whiten", "L", "eps"]
     head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=32)
     assert set(head.state_dict()) == {"pool.p", "whiten.weight", "whiten.bias"}
     assert float(head.whiten.bias.abs().max()) == 0.0 and float(head.whiten.weight.std()) < 0.05
