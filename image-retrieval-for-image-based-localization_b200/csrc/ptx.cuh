@@ -29,6 +29,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#ifdef CIR_MBAR_SUSPEND_NS
+    // experiment: let the hardware keep a waiting thread suspended longer (fewer wake-ups of the polling loop)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)CIR_MBAR_SUSPEND_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -36,6 +46,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok;
 }
 // Bounded wait: a protocol bug must trap (the host sees a launch error) instead of hanging

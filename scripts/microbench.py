@@ -224,3 +224,35 @@ if what == "smid":
     bysm = {}
     for c in range(148): bysm.setdefault(int(smid[0][c]) // 2 // 9, []).append(m[c])
     print("smid: mean by group of 18 SMs:", {k: round(float(np.mean(v)), 1) for k, v in sorted(bysm.items())})
+if what == "interleave":
+    # does a cooperative tail launch cost more right after an ordinary kernel (the real pipeline: backbone -> tail)?
+    from bench import make_head
+    B, C, H, W = 64, 2048, 32, 32
+    head = make_head(dev)
+    xs = [torch.relu(torch.randn((B, C, H, W), device=dev)) for _ in range(2)]
+    small = torch.zeros(1024, device=dev)
+    big = torch.randn((64, 2048, 32, 32), device=dev)
+    i = [0]
+    def tail_only():
+        i[0] ^= 1
+        with torch.no_grad(): head(xs[i[0]])
+    def small_only(): small.add_(1.0)
+    def tail_small():
+        tail_only(); small.add_(1.0)
+    def relu_only(): torch.relu_(big)
+    def tail_relu():
+        tail_only(); torch.relu_(big)
+    for name, fn in [("tail", tail_only), ("small kernel", small_only), ("tail + small kernel", tail_small),
+                     ("relu 512MiB", relu_only), ("tail + relu 512MiB", tail_relu)]:
+        ms = timeit(fn, n=50, warm=5)
+        print(f"interleave {name:24s} {ms*1e3:8.1f} us per iteration")
+    # first steps after an idle gap
+    import time as _t
+    for gap in (0.0, 0.002, 0.05):
+        torch.cuda.synchronize(); _t.sleep(gap)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
+        evs[0].record()
+        for k in range(12):
+            tail_only(); evs[k + 1].record()
+        torch.cuda.synchronize()
+        print(f"interleave after {gap*1e3:.0f} ms idle, per-step us:", [round(evs[k].elapsed_time(evs[k + 1]) * 1e3, 1) for k in range(12)])
