@@ -129,6 +129,54 @@ class ShardedIndex:
         return merge_topk(buf[:, 0].view(torch.float32), buf[:, 1], k)
 
 
+def all_gather_rows(local_rows: torch.Tensor, n_global: int, group=None) -> torch.Tensor:
+    """Row shards (rank r holds rows shard_bounds(n_global, W, r)) -> the full [n_global, D] matrix on every rank."""
+    rank, ws = world(group)
+    if ws == 1:
+        return local_rows
+    D = local_rows.shape[1]
+    sizes = [shard_bounds(n_global, ws, r)[1] - shard_bounds(n_global, ws, r)[0] for r in range(ws)]
+    mx = max(sizes)
+    pad = local_rows if local_rows.shape[0] == mx else torch.cat(
+        [local_rows, local_rows.new_zeros((mx - local_rows.shape[0], D))], 0)
+    allv = torch.empty((ws * mx, D), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(allv, pad.contiguous(), group=group)
+    if all(sz == mx for sz in sizes):
+        return allv
+    allv = allv.view(ws, mx, D)
+    return torch.cat([allv[r, :sizes[r]] for r in range(ws)], 0)
+
+
+def alpha_qe_sharded_rows(q_rows, sharded: "ShardedIndex", k=10, alpha=3.0):
+    """alpha-QE against a ROW-SHARDED database (BASELINE.json config 5): one sharded search for the global top-k lists, every
+    rank sums the neighbours that live in its shard (cir_qe_aggregate without the query and without the L2N), ONE
+    all_reduce of the [Q, D] parts, then q' = L2N(q + sum).  Every rank returns all expanded queries."""
+    from .rerank import qe_aggregate_rows
+    from . import functional as LF
+    if sharded.index.rows32 is None:
+        raise ValueError("alpha-QE needs the fp32 database rows (keep_fp32=True)")
+    s, i = sharded.search_rows(q_rows, k)
+    mine = (i >= sharded.lo) & (i < sharded.hi)
+    i_loc = torch.where(mine, i - sharded.lo, torch.full_like(i, -1))
+    part = qe_aggregate_rows(None, sharded.index.rows32, i_loc, s, k, alpha, normalize=False)
+    if sharded.world_size > 1:
+        dist.all_reduce(part, group=sharded.group)
+    return LF.l2n(q_rows + part)
+
+
+def dba_sharded_rows(local_rows, n_global, k=10, alpha=3.0, group=None, mode="bf16", chunk=16384):
+    """Database-side augmentation of a row-sharded database: the rows are replicated once (one all_gather; 1M x 2048 fp32 =
+    8.2 GB + 4.1 GB bf16 per GPU), then every rank augments ITS OWN rows against the whole database with no further
+    communication.  Returns this rank's augmented rows [hi - lo, D]."""
+    from .rerank import dba_rows
+    from .search import Index
+    rank, ws = world(group)
+    lo, hi = shard_bounds(n_global, ws, rank)
+    full = all_gather_rows(local_rows, n_global, group)
+    index = Index(full, mode=mode)
+    return dba_rows(full, k, alpha, index=index, row_begin=lo, row_end=hi, chunk=chunk)
+
+
 def extract_vectors_dp(net, images, group=None, **kw):
     """Data-parallel extract_vectors: every rank returns the full D x N matrix (on its device)."""
     from .extract import extract_vectors

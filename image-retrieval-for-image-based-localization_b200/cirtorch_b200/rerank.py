@@ -14,20 +14,25 @@ from . import _lib
 from .search import Index, _rows, _check_rows
 
 
-def qe_aggregate_rows(q_rows, db_rows, idx, scores, k_use, alpha, self_base=-1, idx_offset=0, eps=1e-6):
-    _check_rows(q_rows)
+def qe_aggregate_rows(q_rows, db_rows, idx, scores, k_use, alpha, self_base=-1, idx_offset=0, eps=1e-6, normalize=True):
+    """cir_qe_aggregate.  ``q_rows=None`` and ``normalize=False`` give the raw neighbour sum of one database shard
+    (entries that live in other shards masked to -1): parts are added across ranks and normalised afterwards."""
     _check_rows(db_rows)
     lib = _lib.load()
-    Q, D = q_rows.shape
     idx = idx.to(torch.int32)
     if idx_offset:
         idx = torch.where(idx >= 0, idx - idx_offset, idx)
     idx = idx.contiguous()
     scores = scores.float().contiguous()
-    out = torch.empty_like(q_rows)
+    Q, D = idx.shape[0], db_rows.shape[1]
+    if q_rows is not None:
+        _check_rows(q_rows)
+        if tuple(q_rows.shape) != (Q, D):
+            raise ValueError("queries are %s, lists / database say %d x %d" % (tuple(q_rows.shape), Q, D))
+    out = torch.empty((Q, D), dtype=torch.float32, device=db_rows.device)
     rc = lib.cir_qe_aggregate(_lib.ptr(q_rows), Q, _lib.ptr(db_rows), db_rows.shape[0], D, _lib.ptr(idx),
                               _lib.ptr(scores), idx.shape[1], idx.shape[1], int(k_use), float(alpha), int(self_base),
-                              float(eps), _lib.ptr(out), _lib.stream_of(q_rows))
+                              float(eps) if normalize else -1.0, _lib.ptr(out), _lib.stream_of(db_rows))
     _lib.check(rc, "cir_qe_aggregate")
     return out
 

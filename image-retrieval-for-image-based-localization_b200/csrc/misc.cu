@@ -83,7 +83,7 @@ qe_aggregate_kernel(const float* __restrict__ q32, const float* __restrict__ db3
     // each thread owns elements d = tid, tid + 256, ... (kept in global `out` between passes)
     float ss = 0.0f;
     for (int d = tid; d < D; d += QE_THREADS) {
-        float acc = __ldg(q32 + (size_t)q * D + d);
+        float acc = q32 ? __ldg(q32 + (size_t)q * D + d) : 0.0f;      // q32 == NULL: the neighbour sum alone (one shard's part)
         int used = 0;
         for (int i = 0; i < klist && used < k_use; ++i) {
             const int32_t ix = __ldg(idx + (size_t)q * ld_k + i);
@@ -106,6 +106,7 @@ qe_aggregate_kernel(const float* __restrict__ q32, const float* __restrict__ db3
         s_tot = t;
     }
     __syncthreads();
+    if (eps_l2 < 0.0f) return;                            // raw sum: the caller adds the shards' parts, then normalises
     const float denom = sqrtf(s_tot) + eps_l2;
     for (int d = tid; d < D; d += QE_THREADS) out[(size_t)q * D + d] /= denom;
 }
@@ -235,7 +236,7 @@ extern "C" int cir_bias_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, 
 extern "C" int cir_qe_aggregate(const float* q32, int Q, const float* db32, int64_t N, int D, const int32_t* idx,
                                 const float* scores, int klist, int ld_k, int k_use, float alpha, int64_t self_base,
                                 float eps_l2, float* out, void* stream) {
-    CIR_REQUIRE(q32 && db32 && idx && scores && out, CIR_ERR_INVALID_ARG, "cir_qe_aggregate: null pointer");
+    CIR_REQUIRE(db32 && idx && scores && out, CIR_ERR_INVALID_ARG, "cir_qe_aggregate: null pointer");
     CIR_REQUIRE(Q >= 0 && N > 0 && D > 0 && klist >= 0 && ld_k >= klist && k_use >= 0, CIR_ERR_INVALID_ARG,
                 "cir_qe_aggregate: bad shape");
     if (Q == 0) return CIR_OK;

@@ -189,6 +189,8 @@ int cir_rescore_topk(const float* q32, int Q, const float* db32, int64_t N, int 
  *    over the first k_use usable entries of the query's neighbour list idx[q, 0:klist):
  *    entries with idx < 0, and the self match idx == self_base + q (when self_base >= 0,
  *    database-side augmentation), are skipped and do not count.  out [Q, D] fp32.
+ *    Row-sharded databases: q32 == NULL starts from zero and eps_l2 < 0 skips the L2N, which gives the sum over the
+ *    neighbours of ONE shard (entries of other shards masked to -1); the parts are added (all_reduce) and normalised after.
  * ------------------------------------------------------------------------------------ */
 int cir_qe_aggregate(const float* q32, int Q, const float* db32, int64_t N, int D,
                      const int32_t* idx, const float* scores, int klist, int ld_k, int k_use,

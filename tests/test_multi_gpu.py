@@ -1,5 +1,5 @@
-"""Two-GPU NCCL / NVLink tests of the sharded search (skipped on a single-GPU box):
-NCCL all_gather path and the fused peer-store exchange must both equal the single-GPU result."""
+"""Two-GPU NCCL / NVLink tests (skipped on a single-GPU box): the sharded search (NCCL all_gather path and the fused
+peer-store exchange) and the sharded alpha-QE / DBA must equal the single-GPU results."""
 import os
 import sys
 
@@ -35,6 +35,17 @@ def _worker(rank, world, port, out):
     for _ in range(3):                                               # alternates the two exchange buffers
         s2, i2 = sh.search_packed_p2p(qp, k)                         # fused peer-store exchange
         ok = ok and bool(torch.equal(i2, i_ref)) and bool(torch.equal(s2, s_ref))
+    # config 5 on shards: alpha-QE with the neighbour sum split over the ranks, DBA with each rank augmenting its rows
+    from cirtorch_b200 import rerank as R
+    full_index = S.Index(db, mode="bf16")
+    q2_ref = R.alpha_qe_rows(q, full_index, k=10, alpha=3.0)
+    q2 = P.alpha_qe_sharded_rows(q, sh, k=10, alpha=3.0)
+    ok = ok and float((q2 - q2_ref).abs().max()) < 2e-6
+    small = db[:6000].contiguous()
+    lo2, hi2 = P.shard_bounds(6000, world, rank)
+    aug_ref = R.dba_rows(small, k=10, alpha=3.0)
+    aug = P.dba_sharded_rows(small[lo2:hi2].contiguous(), 6000, k=10, alpha=3.0)
+    ok = ok and aug.shape == (hi2 - lo2, D) and float((aug - aug_ref[lo2:hi2]).abs().max()) < 2e-6
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()
