@@ -37,6 +37,9 @@ def _worker(rank, world, port, out):
     merged = np.take_along_axis(iu, order, 1)
     s_ref, i_ref = O.topk(db.T, q.T, k)
     ok = bool((merged == i_ref.T).all())
+    # row shards -> the replicated matrix (ragged: 500 + 501 rows), the plumbing of the sharded DBA / DP extraction
+    full = P.all_gather_rows(torch.from_numpy(db[lo:hi].copy()), N)
+    ok = ok and tuple(full.shape) == (N, D) and bool((full.numpy() == db).all())
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

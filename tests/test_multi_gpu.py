@@ -46,6 +46,25 @@ def _worker(rank, world, port, out):
     aug_ref = R.dba_rows(small, k=10, alpha=3.0)
     aug = P.dba_sharded_rows(small[lo2:hi2].contiguous(), 6000, k=10, alpha=3.0)
     ok = ok and aug.shape == (hi2 - lo2, D) and float((aug - aug_ref[lo2:hi2]).abs().max()) < 2e-6
+    # data-parallel extraction: every rank extracts its slice of the images, one all_gather of the descriptor rows
+    from cirtorch_b200.extract import ImageRetrievalNet, extract_vectors
+    from cirtorch_b200.modules.heads.global_head import globalHead
+
+    class Body(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 64, 3, padding=1)
+
+        def forward(self, img):
+            return {"mod5": torch.relu(self.conv(img))}
+
+    torch.manual_seed(11)
+    net = ImageRetrievalNet(Body(), globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}},
+                                               normal={"name": "L2N", "params": {}}, dim=64)).to(dev).eval()
+    imgs = [torch.randn(3, 40, 32, generator=g) for _ in range(7)]
+    v_ref = extract_vectors(net, imgs, 40, None, batch_size=2, device=dev)            # D x 7 on the CPU, like upstream
+    v_dp = P.extract_vectors_dp(net, imgs, image_size=40, transform=None, batch_size=2, device=dev)
+    ok = ok and tuple(v_dp.shape) == (64, 7) and float((v_dp.cpu() - v_ref).abs().max()) < 1e-6
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     torch.cuda.synchronize()
