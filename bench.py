@@ -356,17 +356,20 @@ def bench_search(dev, rank, world, pk, steps, warmup):
             s_host = torch.empty((Q, TOPK), dtype=torch.float32).pin_memory()
             i_host = torch.empty((Q, TOPK), dtype=torch.int32).pin_memory()
 
+            sh_e2e = P.ShardedIndex.__new__(P.ShardedIndex)
+            sh_e2e._exchange, sh_e2e.group, sh_e2e.rank, sh_e2e.world_size, sh_e2e.lo, sh_e2e.hi, sh_e2e.n_global = \
+                {}, None, rank, world, lo, hi, DB_N
+            sh_e2e.index = index
+
             def step_e2e():
-                qd = q_host.to(dev, non_blocking=True)
-                s, i = index.search_rows(qd, TOPK)            # bf16 scan of top-128 + exact fp32 re-score
-                if world > 1:
-                    s_all, i_all = P.gather_topk(s, i)
-                    s, i = S.merge_topk(s_all, i_all, TOPK)
+                # every rank needs all queries: each copies 1/G of them over PCIe, one all_gather over NVLink
+                qd = P.replicate_host_rows(q_host, dev)
+                s, i = sh_e2e.search_rows(qd, TOPK)           # bf16 scan, global top-128, exact fp32 re-score, merge
                 s_host.copy_(s, non_blocking=True)
                 i_host.copy_(i, non_blocking=True)
 
             ms_e = timed_region(step_e2e, k_steps, 3, world) / k_steps
-            res["e2e"] = {"value": Q / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * DB_D * 4,
+            res["e2e"] = {"value": Q / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * DB_D * 4 // world,
                           "d2h_bytes_per_step": Q * TOPK * 8, "includes": "fp32 re-score of 128 candidates"}
         out[name] = res
         del q32, qp

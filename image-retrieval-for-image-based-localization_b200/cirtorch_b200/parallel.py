@@ -97,13 +97,28 @@ class ShardedIndex:
         return self.index.search_rows(q_rows, k, rescore=rescore)
 
     def search_rows(self, q_rows, k, rescore=None):
-        """Global top-k on every rank: (scores [Q, k], idx [Q, k] global row ids)."""
-        from .search import merge_topk
-        s, i = self.search_local(q_rows, k, rescore=rescore)
+        """Global top-k on every rank: (scores [Q, k], idx [Q, k] global row ids).
+
+        With re-scoring (the default for a bf16 index that keeps its fp32 rows) the result is exactly what one GPU holding the
+        whole database returns: the shards' bf16 lists of k + 28 candidates are merged into the GLOBAL bf16 candidate list,
+        every rank re-scores in fp32 only the candidates that live in its shard (1/G of the gather traffic instead of a full
+        list per shard), and a second all_gather + merge orders them."""
+        from .search import MAX_K, merge_topk, rescore_pad, rescore_rows
+        if rescore is None:
+            rescore = self.index.mode == "bf16" and self.index.rows32 is not None
         if self.world_size == 1:
-            return s, i
+            return self.index.search_rows(q_rows, k, rescore=rescore)
+        if not rescore:
+            s, i = self.index.search_rows(q_rows, k, rescore=False)
+            s_all, i_all = gather_topk(s, i, self.group)
+            return merge_topk(s_all, i_all, k)      # strided views of the gathered buffer, merged in place
+        kc = min(rescore_pad(k), max(k, self.n_global), MAX_K)
+        s, i = self.index.search_rows(q_rows, kc, rescore=False)
         s_all, i_all = gather_topk(s, i, self.group)
-        return merge_topk(s_all, i_all, k)      # strided views of the gathered buffer, merged in place
+        _, cand = merge_topk(s_all, i_all, kc)       # the global bf16 top-kc, identical on every rank
+        s2, i2 = rescore_rows(q_rows, self.index.rows32, cand, kc, idx_offset=self.lo)    # rows of other shards are skipped
+        s_all, i_all = gather_topk(s2, i2, self.group)
+        return merge_topk(s_all, i_all, k)
 
     def search_packed_p2p(self, qp, k):
         """Global top-k of packed queries with the exchange fused into the search: every rank's selection kernel
@@ -145,6 +160,17 @@ def all_gather_rows(local_rows: torch.Tensor, n_global: int, group=None) -> torc
         return allv
     allv = allv.view(ws, mx, D)
     return torch.cat([allv[r, :sizes[r]] for r in range(ws)], 0)
+
+
+def replicate_host_rows(host_rows: torch.Tensor, device, group=None) -> torch.Tensor:
+    """Host rows (pinned, the same on every rank) -> device rows on every rank, moving each row over PCIe ONCE per node:
+    rank r copies its 1/G slice host -> device, one all_gather over NVLink rebuilds the matrix."""
+    rank, ws = world(group)
+    if ws == 1:
+        return host_rows.to(device, non_blocking=True)
+    n = host_rows.shape[0]
+    lo, hi = shard_bounds(n, ws, rank)
+    return all_gather_rows(host_rows[lo:hi].to(device, non_blocking=True), n, group)
 
 
 def alpha_qe_sharded_rows(q_rows, sharded: "ShardedIndex", k=10, alpha=3.0):

@@ -31,6 +31,12 @@ def _worker(rank, world, port, out):
     sh = P.ShardedIndex(db[lo:hi].contiguous(), N, mode="bf16")
     s1, i1 = sh.search_rows(q, k, rescore=False)                      # NCCL all_gather + merge
     ok = bool(torch.equal(i1, i_ref)) and bool(torch.equal(s1, s_ref))
+    # with fp32 re-scoring the sharded search returns exactly what one GPU holding the whole database returns
+    s_rr, i_rr = S.Index(db, mode="bf16").search_rows(q, k)
+    s3, i3 = sh.search_rows(q, k)
+    ok = ok and bool(torch.equal(i3, i_rr)) and bool(torch.equal(s3, s_rr))
+    qh = q.cpu().pin_memory()
+    ok = ok and bool(torch.equal(P.replicate_host_rows(qh, dev), q))
     qp = S.pack_rows(q, "query", "bf16")
     for _ in range(3):                                               # alternates the two exchange buffers
         s2, i2 = sh.search_packed_p2p(qp, k)                         # fused peer-store exchange
