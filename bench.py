@@ -369,8 +369,10 @@ def bench_search(dev, rank, world, pk, steps, warmup):
                 i_host.copy_(i, non_blocking=True)
 
             ms_e = timed_region(step_e2e, k_steps, 3, world) / k_steps
-            res["e2e"] = {"value": Q / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * DB_D * 4 // world,
-                          "d2h_bytes_per_step": Q * TOPK * 8, "includes": "fp32 re-score of 128 candidates"}
+            res["e2e"] = {"value": Q / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * DB_D * 4,
+                          "d2h_bytes_per_step": world * Q * TOPK * 8,
+                          "includes": "whole job: every query row crosses PCIe once (1/G per rank + all_gather over NVLink), every rank "
+                                      "reads the final lists back; fp32 re-score of 128 candidates"}
         out[name] = res
         del q32, qp
     del dbp, rows32
