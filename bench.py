@@ -443,7 +443,7 @@ def main():
     e_steps = max(3, min(args.steps, 10))
     ms_e = timed_region(step_e2e, e_steps, 3, world)
     e2e = {"value": world * B * e_steps / (ms_e * 1e-3), "unit": "descriptors/s",
-           "h2d_bytes_per_step": B * C * H * W * 4, "d2h_bytes_per_step": B * DOUT * 4}
+           "h2d_bytes_per_step": world * B * C * H * W * 4, "d2h_bytes_per_step": world * B * DOUT * 4}     # whole job
     del x_host, x_dev
     achieved = TAIL_BYTES / (ms_step * 1e-3) / 1e9
 
