@@ -35,6 +35,7 @@ SIGNATURES = {
     "cir_region_pool": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _c_f, _c_int, _vp, _vp]),
     "cir_l2n_rows": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _c_f, _vp, _c_i64, _vp]),
     "cir_pack_bf16": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "cir_search_plan": (_c_int, [_c_int, _c_i64, _c_int, _c_int, _vp]),
     "cir_search_workspace_bytes": (_c_int, [_c_int, _c_i64, _c_int, _c_int, _szp]),
     "cir_search_topk": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp,
                                  C.c_int32, _vp, C.c_size_t, C.c_uint, _vp]),

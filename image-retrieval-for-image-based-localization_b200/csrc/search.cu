@@ -827,6 +827,18 @@ static SearchWs search_ws_layout(const SearchPlan& plan, int Q, int cap, int n0)
     return w;
 }
 
+// Host-only view of the planner (no device needed): how a search of Q queries over N rows is cut into work units on a GPU
+// with num_sms SMs, the candidate-list capacity for k and the size of the threshold sample.
+extern "C" int cir_search_plan(int Q, int64_t N, int k, int num_sms, int32_t* out8) {
+    CIR_REQUIRE(out8 && Q > 0 && N > 0 && k >= 1 && k <= SEARCH_MAX_K && num_sms > 0, CIR_ERR_INVALID_ARG,
+                "cir_search_plan: bad arguments (Q=%d N=%lld k=%d num_sms=%d)", Q, (long long)N, k, num_sms);
+    const SearchPlan p = plan_search(Q, N, num_sms);
+    out8[0] = p.mt; out8[1] = p.nt; out8[2] = p.S; out8[3] = p.tps; out8[4] = p.units; out8[5] = p.Qpad;
+    out8[6] = search_cap_for_k(k);
+    out8[7] = sample_rows(Q, N, k);
+    return CIR_OK;
+}
+
 extern "C" int cir_search_workspace_bytes(int Q, int64_t N, int Kd, int k, size_t* bytes) {
     (void)Kd;
     CIR_REQUIRE(bytes && Q > 0 && N > 0 && k >= 1 && k <= SEARCH_MAX_K, CIR_ERR_INVALID_ARG,

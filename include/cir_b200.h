@@ -133,6 +133,9 @@ int cir_l2n_rows(const float* X, int64_t N, int C, int64_t ldx, float eps,
 int cir_pack_bf16(const float* src, int64_t rows, int D, int64_t src_ld,
                   void* dst, int64_t dst_ld, int n_split, int role, void* stream);
 
+/* host-only planner view (no device needed): out8 = {query tiles, database tiles, splits, tiles per split, work units,
+ * padded query count, candidate-list capacity for k, rows of the threshold pre-pass (0 = none)} for a GPU with num_sms SMs */
+int cir_search_plan(int Q, int64_t N, int k, int num_sms, int32_t* out8);
 int cir_search_workspace_bytes(int Q, int64_t N, int Kd, int k, size_t* bytes);
 /*  q   device bf16 [Q, Kd] (ld = Kd), db device bf16 [N, Kd]; Kd % 64 == 0; 1 <= k <= 512
  *  tau0      optional device [Q] fp32: a caller-supplied lower bound of each query's k-th

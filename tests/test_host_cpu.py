@@ -73,7 +73,7 @@ def test_registries_and_signatures_mirror_reference():
     assert list(inspect.signature(Rpool.__init__).parameters)[1:] == ["rpool", "whiten", "L", "eps"]
     head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=32)
     assert set(head.state_dict()) == {"pool.p", "whiten.weight", "whiten.bias"}
-    assert float(head.whiten.bias.abs().max()) == 0.0 and float(head.whiten.weight.std()) < 0.05
+    assert float(head.whiten.bias.detach().abs().max()) == 0.0 and float(head.whiten.weight.detach().std()) < 0.05
 
 
 def test_shard_bounds_partition():
@@ -139,3 +139,29 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config"):
         assert key in line
+
+
+def test_search_planner_invariants():
+    """cir_search_plan is pure host logic: every database tile belongs to exactly one split, the unit count and the
+    padding follow from the tiles, the list capacity leaves room beyond k, and the threshold sample obeys its rule."""
+    import ctypes as C
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    out = (C.c_int32 * 8)()
+    for num_sms in (148, 132, 16):
+        for Q in (1, 70, 128, 129, 1000, 2049, 10_000):
+            for N in (1, 255, 4993, 8192, 20_000, 65_536, 125_000, 1_000_000, 3_000_001):
+                for k in (1, 10, 100, 512):
+                    assert lib.cir_search_plan(Q, N, k, num_sms, C.cast(out, C.c_void_p)) == 0
+                    mt, nt, S, tps, units, Qpad, cap, n0 = list(out)
+                    assert mt == -(-Q // 128) and nt == -(-N // 256) and Qpad == mt * 128
+                    assert S >= 1 and tps >= 1 and S * tps >= nt and (S - 1) * tps < nt and units == mt * S
+                    assert cap & (cap - 1) == 0 and cap >= k + 96 and cap <= 1024
+                    if n0:
+                        assert N >= 8192 and n0 % 256 == 0 and 1024 <= n0 <= 32768 and 2 * n0 <= N
+                        assert n0 // 8 >= 2 * k                      # at least 2 k groups of 8 rows
+                        assert not (Q <= 128 and N < 65_536)
+                    else:
+                        assert N < 8192 or (Q <= 128 and N < 65_536) or k > 64     # small, single-tile, or k too large for N
+    assert lib.cir_search_plan(0, 10, 1, 148, C.cast(out, C.c_void_p)) != 0
+    assert b"cir_search_plan" in lib.cir_last_error()
