@@ -111,7 +111,7 @@ def test_store_formats_roundtrip(tmp_path):
     sd["whiten.bias"] = torch.zeros(3)                     # wrong shape: skipped like _load_pretraining_dict
     torch.save({"config": "", "state_dict": {"ret_head": sd, "body": {}}, "training_meta": {"epoch": 7}}, tmp_path / "snap.pth")
     meta = store.load_ret_head(str(tmp_path / "snap.pth"), head)
-    assert meta["epoch"] == 7 and float(head.pool.p) == 4.0 and float(head.whiten.bias.abs().max()) == 0.0
+    assert meta["epoch"] == 7 and float(head.pool.p.detach()) == 4.0 and float(head.whiten.bias.detach().abs().max()) == 0.0
 
 
 def test_rmac_region_grid_matches_fixture(golden):
@@ -165,3 +165,31 @@ def test_search_planner_invariants():
                         assert N < 8192 or (Q <= 128 and N < 65_536) or k > 64     # small, single-tile, or k too large for N
     assert lib.cir_search_plan(0, 10, 1, 148, C.cast(out, C.c_void_p)) != 0
     assert b"cir_search_plan" in lib.cir_last_error()
+
+
+def test_entry_points_validate_before_touching_the_device():
+    """Error behaviour of the C ABI without a GPU: null pointers / bad shapes come back as CIR_ERR_INVALID_ARG (-1) with a
+    message naming the entry point -- the checks run before any CUDA call, so no compute is attempted here."""
+    import ctypes as C
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    assert lib.cir_version() >= 100 and lib.cir_launch_count(0) >= 0
+    need = C.c_size_t(0)
+    assert lib.cir_tail_workspace_bytes(0, 2048, 2048, C.byref(need)) == -1
+    assert lib.cir_tail_workspace_bytes(64, 2048, 2048, C.byref(need)) == 0 and need.value > 64 * 2048 * 4
+    calls = {
+        "cir_tail_fwd": lambda: lib.cir_tail_fwd(None, 1, 8, 4, 4, None, 0, 1e-6, 1e-6, 0, None, None, 8, None, 8, None, 0, 0, None),
+        "cir_gem_bwd": lambda: lib.cir_gem_bwd(None, 1, 8, 4, 4, None, 0, 1e-6, None, None, None, None, None),
+        "cir_region_pool": lambda: lib.cir_region_pool(None, 1, 8, 4, 4, None, 1, None, 0, 1e-6, 0, None, None),
+        "cir_l2n_rows": lambda: lib.cir_l2n_rows(None, 1, 8, 8, 1e-6, None, 8, None),
+        "cir_pack_bf16": lambda: lib.cir_pack_bf16(None, 1, 8, 8, None, 64, 1, 0, None),
+        "cir_search_workspace_bytes": lambda: lib.cir_search_workspace_bytes(0, 10, 64, 5, C.byref(need)),
+        "cir_topk_merge": lambda: lib.cir_topk_merge(None, None, 2, 4, 5, 0, None, None, 5, None),
+        "cir_rescore_topk": lambda: lib.cir_rescore_topk(None, 1, None, 10, 8, None, 4, 0, None, None, 2, None),
+        "cir_qe_aggregate": lambda: lib.cir_qe_aggregate(None, 1, None, 10, 8, None, None, 4, 4, 2, 3.0, -1, 1e-6, None, None),
+        "cir_mine_filter": lambda: lib.cir_mine_filter(None, 1, 4, None, 10, None, 2, None, None, 8, None, None, None, None),
+        "cir_eval_ap": lambda: lib.cir_eval_ap(None, 1, 4, 4, None, None, None, None, None, 0, None, None, None),
+    }
+    for name, call in calls.items():
+        assert call() == -1, name
+        assert name.encode() in lib.cir_last_error(), (name, lib.cir_last_error())
