@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: runs a few launches of one hot kernel at its BASELINE.json size.
-    python scripts/profile_target.py tail|search10k|search70|regions|mining [n_launches]
+    python scripts/profile_target.py tail|search10k|search70|regions|bwd|mining [n_launches]
 """
 import os
 import sys
@@ -46,6 +46,14 @@ elif what == "regions":
     p3 = torch.full((1,), 3.0, device=dev)
     for i in range(n):
         LF.region_pool(x, regs, p=p3, pooling="GeM")
+elif what == "bwd":
+    from cirtorch_b200.functional import _gem_bwd_launch
+    x = torch.relu(torch.randn((64, 2048, 32, 32), device=dev))
+    gg = torch.rand((64, 2048), device=dev) + 0.1
+    dg = torch.randn((64, 2048), device=dev)
+    pt = torch.full((1,), 3.0, device=dev)
+    for i in range(n):
+        _gem_bwd_launch(x, pt, 1e-6, gg, dg, True, True)
 elif what == "mining":
     from cirtorch_b200.mining import mine_hard_negatives_rows
     q = torch.randn((2000, 2048), device=dev)
