@@ -3,6 +3,10 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef CIR_MBAR_SUSPEND_NS
+#define CIR_MBAR_SUSPEND_NS 20000      // 0 = plain mbarrier.try_wait
+#endif
+
 namespace cir {
 namespace ptx {
 
@@ -29,8 +33,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-#ifdef CIR_MBAR_SUSPEND_NS
-    // experiment: let the hardware keep a waiting thread suspended longer (fewer wake-ups of the polling loop)
+#if CIR_MBAR_SUSPEND_NS > 0
+    // suspend-time hint: the hardware may keep the waiting thread parked up to this long before the probe returns (it is
+    // woken as soon as the phase completes), so the idle roles (producer, MMA issuer, epilogue between tiles) wake up and
+    // re-issue the polling loop less often.  A/B on B200, three runs each: tail 100.2-100.7 -> 99.7 us, 10k x 1M search
+    // 32.3-33.4 -> 32.0-32.8 ms, 70 x 1M unchanged.
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
