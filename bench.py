@@ -30,7 +30,7 @@ import torch
 
 B, C, H, W, DOUT = 64, 2048, 32, 32, 2048
 TAIL_BYTES = B * C * H * W * 4 + DOUT * C * 4 + DOUT * 4 + B * DOUT * 4          # 554,180,608
-TAIL_NCU_TRAFFIC = 553_773_312 + 4_199_936      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r1g_tail.txt)
+TAIL_NCU_TRAFFIC = 553_768_448 + 4_396_288      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r1h_tail.txt)
 DB_N, DB_D, TOPK = 1_000_000, 2048, 100
 METRIC = "descriptors/s (GeM+whiten tail) & queries/s vs 1M×2048 DB at 1/2/4/8 B200, %roofline"
 
@@ -467,7 +467,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": TAIL_NCU_TRAFFIC,
                          "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth; "
-                                 "traffic = dram read+write per launch from profiles/r1g_tail.txt" % pk["src"]},
+                                 "traffic = dram read+write per launch from profiles/r1h_tail.txt" % pk["src"]},
             "search": search,
         }
         if not args.no_cpu_baseline and world == 1:
