@@ -40,6 +40,9 @@ def _worker(rank, world, port, out):
     # row shards -> the replicated matrix (ragged: 500 + 501 rows), the plumbing of the sharded DBA / DP extraction
     full = P.all_gather_rows(torch.from_numpy(db[lo:hi].copy()), N)
     ok = ok and tuple(full.shape) == (N, D) and bool((full.numpy() == db).all())
+    # host rows replicated with one slice per rank + all_gather (the end-to-end query path of the sharded search)
+    rep = P.replicate_host_rows(torch.from_numpy(q.copy()), torch.device("cpu"))
+    ok = ok and tuple(rep.shape) == (Q, D) and bool((rep.numpy() == q).all())
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
