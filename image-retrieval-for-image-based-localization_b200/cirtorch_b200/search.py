@@ -63,9 +63,14 @@ def pack_rows(x_rows: torch.Tensor, role: str, mode: str = "bf16", out: torch.Te
     return out
 
 
+NO_PREPASS, SAMPLE_FIRST_ROWS = 1, 2        # flags of cir_search_topk (include/cir_b200.h)
+
+
 def search_packed(qp: torch.Tensor, dbp: torch.Tensor, k: int, idx_offset: int = 0, tau0=None,
-                  q_label=None, db_label=None, out=None):
-    """Top-k of packed operands: (scores [Q, k] fp32, idx [Q, k] int32), sorted (score desc, idx asc)."""
+                  q_label=None, db_label=None, out=None, flags: int = 0):
+    """Top-k of packed operands: (scores [Q, k] fp32, idx [Q, k] int32), sorted (score desc, idx asc).
+
+    ``flags``: NO_PREPASS / SAMPLE_FIRST_ROWS change how the running thresholds are warm-started, never the result."""
     _lib.require_cuda(qp, dbp, tau0, q_label, db_label)
     lib = _lib.load()
     Q, Kd = qp.shape
@@ -93,7 +98,7 @@ def search_packed(qp: torch.Tensor, dbp: torch.Tensor, k: int, idx_offset: int =
         db_label = db_label.to(torch.int32).contiguous()
     rc = lib.cir_search_topk(_lib.ptr(qp), Q, _lib.ptr(dbp), N, Kd, k, _lib.ptr(tau0), _lib.ptr(q_label),
                              _lib.ptr(db_label), _lib.ptr(scores), _lib.ptr(idx), int(idx_offset),
-                             _lib.ptr(ws), ws.numel(), 0, _lib.stream_of(qp))
+                             _lib.ptr(ws), ws.numel(), int(flags), _lib.stream_of(qp))
     _lib.check(rc, "cir_search_topk")
     return scores, idx
 

@@ -61,6 +61,7 @@ struct SearchParams {
     float* dense_out;            // MODE_DENSE: [Q, dense_ld]
     long long dense_ld;
     int b_policy;                // database tiles: 0 evict_last, 1 evict_first, 2 evict_normal
+    int tile_stride;             // database tile n of the problem is tile n * tile_stride of the matrix (threshold sample: > 1)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -189,7 +190,7 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         uint8_t* a = smem + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
                         tma_load_2d_hint(a, &tmA, &full[stage], kb * BK, m * BM, pol_a);
-                        tma_load_2d_hint(a + A_BYTES, &tmB, &full[stage], kb * BK, n * BN, pol_b);
+                        tma_load_2d_hint(a + A_BYTES, &tmB, &full[stage], kb * BK, n * P.tile_stride * BN, pol_b);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -346,9 +347,10 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         // query's k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.
                         if (valid) {
                             if (LABELS) {                   // mining: rows of the query's own cluster do not count
+                                const int32_t* lab = P.db_label + (long long)n * P.tile_stride * BN + c * 32;   // the sampled tile's rows
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (__ldg(P.db_label + cb + j) == qlab) v[j] = 0xff800000u;      // -inf
+                                    if (__ldg(lab + j) == qlab) v[j] = 0xff800000u;      // -inf
                             }
                             float m[32 / GROUP];
 #pragma unroll
@@ -707,6 +709,7 @@ static int launch_search2(const void* q, int Q, const void* db, long long N, int
     P.kblocks = Kd / BK;
     P.mt = plan.mt; P.nt = plan.nt; P.S = plan.S; P.tps = plan.tps; P.units = plan.units; P.Qpad = plan.Qpad;
     P.b_policy = 0;
+    P.tile_stride = 1;
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -731,21 +734,24 @@ static int launch_search2(const void* q, int Q, const void* db, long long N, int
     return CIR_OK;
 }
 
+// N = rows of the problem; the matrix behind `db` has N_map >= N rows and problem tile n is matrix tile n * tile_stride
+// (tile_stride > 1: the threshold sample takes tiles spread evenly over the whole matrix)
 static int launch_search(int mode, const void* q, int Q, const void* db, long long N, int Kd, SearchParams& P,
-                         const SearchPlan& plan, cudaStream_t stream) {
+                         const SearchPlan& plan, cudaStream_t stream, long long N_map = 0, int tile_stride = 1) {
     const DeviceInfo& dev = device_info();
     CIR_REQUIRE(dev.max_smem_optin >= SMEM_BYTES, CIR_ERR_UNSUPPORTED, "search: device offers %d B shared memory, need %d",
                 dev.max_smem_optin, SMEM_BYTES);
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, q, (uint64_t)Q, (uint64_t)Kd, BM);
     if (rc) return rc;
-    rc = make_tmap(&tmB, db, (uint64_t)N, (uint64_t)Kd, BN);
+    rc = make_tmap(&tmB, db, (uint64_t)(N_map > N ? N_map : N), (uint64_t)Kd, BN);
     if (rc) return rc;
     P.Q = Q;
     P.N = (int)N;
     P.kblocks = Kd / BK;
     P.mt = plan.mt; P.nt = plan.nt; P.S = plan.S; P.tps = plan.tps; P.units = plan.units; P.Qpad = plan.Qpad;
     P.b_policy = plan.mt == 1 ? 1 : 0;
+    P.tile_stride = tile_stride;
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -785,8 +791,8 @@ static int check_operands(const char* who, const void* q, int Q, const void* db,
 
 using namespace cir;
 
-// Warm start of the running thresholds: the k-th best score of every query over (a subset of) the first n0
-// database rows is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
+// Warm start of the running thresholds: the k-th best score of every query over (a subset of) n0 database rows --
+// n0 / 256 whole tiles spread evenly over the matrix -- is a valid lower bound of its k-th best over all rows.  It removes almost all list compactions
 // and most appends (measured 53.6 ms -> 30.9 ms on 10k x 1M with an exact tau0).
 static int sample_rows(int Q, long long N, int k) {
     // Large databases: ~N/32 rows (3 % extra scan), a power of two in [2048, 32768], with at least 4 k groups of 8 rows so
@@ -906,8 +912,11 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
         D.dense_ld = n0 / GROUP;
         D.q_label = q_label;          // mining: the threshold only counts rows the query may take
         D.db_label = db_label;
+        // the sample = n0 / 256 tiles spread evenly over the FULL tiles of the matrix, so that the threshold does not depend
+        // on how the rows are ordered (a database stored scene by scene: its first rows are a handful of scenes)
+        const int stride = (flags & CIR_SEARCH_SAMPLE_FIRST_ROWS) ? 1 : (int)((N / BN) / (n0 / BN));
         rc = launch_search(MODE_GROUPMAX, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
-                           static_cast<cudaStream_t>(stream));
+                           static_cast<cudaStream_t>(stream), N, stride < 1 ? 1 : stride);
         if (rc) return rc;
         rc = launch_row_kth_largest(dense, Q, n0 / GROUP, n0 / GROUP, k, tau, static_cast<cudaStream_t>(stream));
         if (rc) return rc;

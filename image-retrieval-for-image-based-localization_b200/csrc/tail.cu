@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include <cooperative_groups.h>
@@ -48,6 +49,7 @@ constexpr int TAIL_MAX_BARS = 32;
 constexpr int TAIL_MB = 128;                         // images per phase-B pass (UMMA M)
 constexpr int TAIL_BT_BYTES = TAIL_NT * 128;         // one B tile: 128 rows x 64 k bf16, 128 B swizzle (16 KB)
 constexpr int TAIL_W_BYTES = (TAIL_KS / 64) * 2 * TAIL_BT_BYTES;   // hi + lo tiles of a unit's W tile: 128 KB
+constexpr int TAIL_NPOLY_DEFAULT = 2;                 // general exponent: 2 of every 4 ex2 on the FMA pipe
 constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;    // debug time stamps: up to 1024 CTAs x 8 slots
 
 struct TailParams {
@@ -73,6 +75,7 @@ struct TailParams {
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
     int n_slots;       // ring slots
     int w_bytes;       // shared-memory bytes reserved for the W slice
+    int gen_mode;      // exponent class of a non-integer p on vector rows: PM_GENERAL or PM_GENERAL_POLY0 + NPOLY
     unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
 };
 
@@ -92,7 +95,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 }
 
 // exponent classes: small integer p avoids the two MUFU ops per element
-enum { PM_GENERAL = 0, PM_1 = 1, PM_2 = 2, PM_3 = 3, PM_4 = 4, PM_MAX = 5, PM_MEAN = 6 };
+enum { PM_GENERAL = 0, PM_1 = 1, PM_2 = 2, PM_3 = 3, PM_4 = 4, PM_MAX = 5, PM_MEAN = 6,
+       PM_GENERAL_POLY0 = 16 /* + NPOLY in 0..4: vector rows with NPOLY of 4 ex2 on the FMA pipe */ };
 
 template <int PM>
 __device__ __forceinline__ float fold(float acc, float v, float eps, float p) {
@@ -105,8 +109,36 @@ __device__ __forceinline__ float fold(float acc, float v, float eps, float p) {
     if (PM == PM_4) { const float t2 = t * t; return fmaf(t2, t2, acc); }
     return acc + fast_ex2(p * fast_lg2(t));
 }
+// 2^t on the FMA / ALU pipes (no MUFU): t = n + f with n = rne(t) taken from the low mantissa bits of t + 1.5 * 2^23,
+// 2^f by a degree-4 minimax polynomial on [-0.5, 0.5] (max relative error 2.7e-6), 2^n added into the exponent field.
+__device__ __forceinline__ float poly_ex2(float t) {
+    t = fminf(fmaxf(t, -126.0f), 127.0f);
+    const float r = t + 12582912.0f;
+    const float f = t - (r - 12582912.0f);
+    float q = 0.009570102207362652f;
+    q = fmaf(q, f, 0.05591786280274391f);
+    q = fmaf(q, f, 0.240247443318367f);
+    q = fmaf(q, f, 0.6931217908859253f);
+    q = fmaf(q, f, 0.9999992847442627f);
+    return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
+// general exponent, second flavour: lg2 on the MUFU pipe, 2^t on the FMA pipe
+__device__ __forceinline__ float fold_poly(float acc, float v, float eps, float p) {
+    return acc + poly_ex2(p * fast_lg2(fmaxf(v, eps)));
+}
+// General exponent: x^p = ex2(p * lg2 x) costs two MUFU operations per element, and the MUFU pipe (4 lanes per clock and SM
+// sub-partition), not HBM, then bounds the stream (117 us vs 99 us for p = 3 at 64 x 2048 x 32 x 32).  PM_GENERAL + NPOLY sends
+// NPOLY of every 4 ex2 to the FMA pipe instead (poly_ex2), which balances the two pipes.
 template <int PM>
 __device__ __forceinline__ float fold4(float acc, const float4& v, float eps, float p) {
+    if (PM >= PM_GENERAL_POLY0) {
+        constexpr int NPOLY = PM - PM_GENERAL_POLY0;
+        acc = NPOLY >= 4 ? fold_poly(acc, v.x, eps, p) : fold<PM_GENERAL>(acc, v.x, eps, p);
+        acc = NPOLY >= 1 ? fold_poly(acc, v.y, eps, p) : fold<PM_GENERAL>(acc, v.y, eps, p);
+        acc = NPOLY >= 3 ? fold_poly(acc, v.z, eps, p) : fold<PM_GENERAL>(acc, v.z, eps, p);
+        acc = NPOLY >= 2 ? fold_poly(acc, v.w, eps, p) : fold<PM_GENERAL>(acc, v.w, eps, p);
+        return acc;
+    }
     acc = fold<PM>(acc, v.x, eps, p);
     acc = fold<PM>(acc, v.y, eps, p);
     acc = fold<PM>(acc, v.z, eps, p);
@@ -114,14 +146,14 @@ __device__ __forceinline__ float fold4(float acc, const float4& v, float eps, fl
     return acc;
 }
 
-__device__ __forceinline__ int classify_p(int pool_mode, float p) {
+__device__ __forceinline__ int classify_p(int pool_mode, float p, int gen_mode = PM_GENERAL) {
     if (pool_mode == CIR_POOL_MAC) return PM_MAX;
     if (pool_mode == CIR_POOL_SPOC) return PM_MEAN;
     if (p == 3.0f) return PM_3;
     if (p == 2.0f) return PM_2;
     if (p == 1.0f) return PM_1;
     if (p == 4.0f) return PM_4;
-    return PM_GENERAL;
+    return gen_mode;
 }
 
 // per-lane partial of one row held as float4s (shared or global memory), lanes stride the vectors
@@ -165,6 +197,10 @@ __device__ __forceinline__ float row_reduce(int pm, const float* row, int HW, bo
         CIR_ROW_CASE(PM_4)
         CIR_ROW_CASE(PM_MAX)
         CIR_ROW_CASE(PM_MEAN)
+        case PM_GENERAL_POLY0 + 1: a = row_partial_vec<PM_GENERAL_POLY0 + 1, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
+        case PM_GENERAL_POLY0 + 2: a = row_partial_vec<PM_GENERAL_POLY0 + 2, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
+        case PM_GENERAL_POLY0 + 3: a = row_partial_vec<PM_GENERAL_POLY0 + 3, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
+        case PM_GENERAL_POLY0 + 4: a = row_partial_vec<PM_GENERAL_POLY0 + 4, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
         default:
             a = vec ? row_partial_vec<PM_GENERAL, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p)
                     : row_partial_scalar<PM_GENERAL>(row, HW, lane, eps, p);
@@ -180,12 +216,6 @@ __device__ __forceinline__ float finish_row(int pm, float acc, int HW, float p) 
     // reference: .pow(1. / self.p) with the reciprocal rounded to fp32 (pools.py:38)
     return powf(mean, 1.0f / p);
 }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // TMA bulk copy global -> shared (1-D, size % 16 == 0), completes on an mbarrier
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
@@ -220,13 +250,6 @@ __device__ __forceinline__ float sumsq8(const uint4& h, const uint4& l) {
     }
     return s;
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
 // fp32 W tile of projection unit u = (nt, ks) -> bf16 hi / lo UMMA B tiles (K-major, 128 B swizzle):
 // tile (kb, part) at Bt + (kb * 2 + part) * 16 KB, row r at (r / 8) * 1024 + (r % 8) * 128, 16-byte chunk c at
 // ((c ^ (r % 8)) * 16).  One task = one chunk (8 consecutive k of one row); rows >= D_out and k >= C become zeros.
@@ -400,7 +423,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         const long long row = r0 + i;
                         const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
                         const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
-                        const float a = row_reduce<false>(classify_p(P.pool_mode, pr), src, HW, true, lane, P.eps_gem, pr);
+                        const float a = row_reduce<false>(classify_p(P.pool_mode, pr, P.gen_mode), src, HW, true, lane, P.eps_gem, pr);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
                         take(a, row);
@@ -421,7 +444,8 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
             for (int j = warp; j < my_rows; j += TAIL_WARPS) {
                 const long long row = r0 + j;
                 const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
-                const float a = row_reduce<true>(classify_p(P.pool_mode, pr), P.x + row * HW, HW, P.vec_ok != 0, lane, P.eps_gem, pr);
+                const float a = row_reduce<true>(classify_p(P.pool_mode, pr, P.vec_ok ? P.gen_mode : PM_GENERAL), P.x + row * HW, HW, P.vec_ok != 0, lane,
+                                               P.eps_gem, pr);
                 take(a, row);
             }
             flush();
@@ -722,6 +746,12 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.Wt = Wt; P.bias = bias; P.D_out = D_out; P.out = out; P.out_ld = out_ld; P.flags = flags;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
+    {
+        // non-integer exponent: how many of every 4 ex2 go to the FMA pipe (CIR_TAIL_NPOLY = 0..4 for experiments)
+        static const char* dbg = getenv("CIR_TAIL_NPOLY");
+        const int npoly = (dbg && dbg[0] >= '0' && dbg[0] <= '4') ? dbg[0] - '0' : TAIL_NPOLY_DEFAULT;
+        P.gen_mode = npoly == 0 ? PM_GENERAL : PM_GENERAL_POLY0 + npoly;
+    }
 
     const int grid = dev.num_sms;
     if (pool_only) {
