@@ -28,7 +28,7 @@ SIGNATURES = {
     "cir_launch_count": (_c_i64, [_c_int]),
     "cir_tail_workspace_bytes": (_c_int, [_c_int, _c_int, _c_int, _szp]),
     "cir_tail_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _c_f, _c_int,
-                              _vp, _vp, _c_int, _vp, _c_int, _vp, C.c_size_t, C.c_uint, _vp]),
+                              _vp, _vp, _c_int, _vp, _c_int, _vp, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_gem_bwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp]),
     "cir_bias_l2n_rows": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _vp, _c_f, _vp, _c_i64, _vp]),
     "cir_powerlaw": (_c_int, [_vp, _c_i64, _c_f, _vp, _vp]),
@@ -49,6 +49,12 @@ SIGNATURES = {
     "cir_qe_aggregate": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_f, _c_i64,
                                   _c_f, _vp, _vp]),
     "cir_eval_ap": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp]),
+    "cir_tuple_loss_workspace_bytes": (_c_int, [_c_int, _szp]),
+    "cir_tuple_loss": (_c_int, [_vp, _c_i64, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _c_f, _vp, _vp, _c_i64, _vp,
+                                C.c_size_t, _vp]),
+    "cir_l2n_bwd_rows": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_f, _vp, _vp, _vp]),
+    "cir_colsum_rows": (_c_int, [_vp, _c_i64, _c_int, _vp, _vp]),
+    "cir_gem_dp": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "cir_mine_filter": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
 }
 

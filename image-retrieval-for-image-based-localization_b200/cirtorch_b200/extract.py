@@ -75,12 +75,17 @@ def _load(item, image_size, transform, bbx):
 
 @torch.no_grad()
 def extract_vectors(net, images, image_size=1024, transform=None, bbxs=None, ms=(1,), msp=1, batch_size=1,
-                    device=None, rank=0, world_size=1, print_freq=0):
+                    device=None, rank=0, world_size=1, print_freq=0, pad_ragged=False):
     """images: list of image tensors (3 x H x W) / paths, or one B x 3 x H x W tensor -> D x N fp32 (CPU, like upstream).
 
     ``msp`` is accepted for signature compatibility; the fork averages scales without the
     generalized-mean power.  With ``world_size > 1`` rank r extracts the
     contiguous slice [r*n/W, (r+1)*n/W) and the caller all-gathers (parallel.extract_vectors_dp).
+
+    Images of different sizes in one batch: by default every image is run at its own size (one launch per image, the
+    descriptor does not depend on its batch mates).  ``pad_ragged=True`` reproduces the fork instead: the batch is
+    zero-padded to Hmax x Wmax (cirtorch/utils/sequence.py:4-67) and GeM pools over the padding, because
+    ``globalFeatureAlgo.inference`` ignores the valid sizes (GF_algo.py:85-90).
     """
     device = device or next(net.parameters()).device
     net.eval()
@@ -95,6 +100,9 @@ def extract_vectors(net, images, image_size=1024, transform=None, bbxs=None, ms=
         shapes = {tuple(t.shape) for t in items}
         if len(shapes) == 1:
             groups = [(list(range(i, j)), torch.stack(items))]
+        elif pad_ragged:                       # the fork's behaviour: one zero-padded batch
+            from .utils.sequence import PackedSequence, pad_packed_images
+            groups = [(list(range(i, j)), pad_packed_images(PackedSequence(items))[0])]
         else:                                  # ragged sizes: one launch per image
             groups = [([i + t], it[None]) for t, it in enumerate(items)]
         for ids, batch in groups:

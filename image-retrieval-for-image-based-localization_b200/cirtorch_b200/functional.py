@@ -22,8 +22,9 @@ def _as_f32_contig(x: torch.Tensor) -> torch.Tensor:
 _tail_ws_bytes = {}
 
 
-def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None):
+def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None, pooled_out=None):
     """One cooperative launch of the fused tail.  Returns the physical [N, D] buffer.
+    ``pooled_out``: optional contiguous fp32 [N, C] buffer that receives the pooled values (kept for the backward pass).
 
     Kept lean on the host (a launch is ~0.1 ms of GPU time): no detach / reshape copies, one stream query."""
     _lib.require_cuda(x, p, weight, bias)
@@ -68,8 +69,8 @@ def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=Non
     rc = lib.cir_tail_fwd(x.data_ptr(), N, Cc, H, W, p.data_ptr() if p is not None else None, p_stride, eps, l2_eps,
                           pool_mode, weight.data_ptr() if whiten else None,
                           bias.data_ptr() if (whiten and bias is not None) else None, D,
-                          out.data_ptr(), D, ws.data_ptr(), ws.numel(), flags,
-                          torch.cuda.current_stream(x.device).cuda_stream)
+                          out.data_ptr(), D, pooled_out.data_ptr() if pooled_out is not None else None,
+                          ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream(x.device).cuda_stream)
     if rc:
         _lib.check(rc, "cir_tail_fwd")
     return out
@@ -107,34 +108,42 @@ def _gem_bwd_launch(x, p, eps, g, dg, want_dx, want_s):
     return dx, S
 
 
-def _l2n_bwd(v, gout, l2_eps):
-    """Gradient of v / (||v|| + eps) w.r.t. v (rows)."""
-    s = v.norm(p=2, dim=1, keepdim=True)
-    return gout / (s + l2_eps) - v * ((v * gout).sum(dim=1, keepdim=True) / (s * (s + l2_eps) ** 2))
+def _l2n_bwd_rows(v, gout, l2_eps, want_unit=False):
+    """cir_l2n_bwd_rows: gradient of v / (||v|| + eps) w.r.t. v applied to gout (rows); optionally also the forward value."""
+    lib = _lib.load()
+    N, Cc = v.shape
+    out = torch.empty_like(v) if gout is not None else None
+    unit = torch.empty_like(v) if want_unit else None
+    rc = lib.cir_l2n_bwd_rows(_lib.ptr(v), _lib.ptr(gout), N, Cc, float(l2_eps), _lib.ptr(out), _lib.ptr(unit), _lib.stream_of(v))
+    _lib.check(rc, "cir_l2n_bwd_rows")
+    return out, unit
+
+
+def _colsum_rows(x2d):
+    lib = _lib.load()
+    out = torch.empty((x2d.shape[1],), dtype=torch.float32, device=x2d.device)
+    _lib.check(lib.cir_colsum_rows(_lib.ptr(x2d), x2d.shape[0], x2d.shape[1], _lib.ptr(out), _lib.stream_of(x2d)), "cir_colsum_rows")
+    return out
 
 
 class _TailFn(torch.autograd.Function):
-    """Forward = the fused CUDA kernel.  Backward for GeM pooling: the [N, C] / [N, D]-sized chain (two L2Ns, the
-    Linear) in stock torch ops + cuBLAS, and ONE streaming kernel (cir_gem_bwd) for everything that touches the
-    feature map: dx and the sum needed for dL/dp.  MAC / SPoC recompute the tail with differentiable torch ops."""
+    """Forward = the fused CUDA kernel (which also hands back the pooled values g).  Backward for GeM pooling: two
+    row kernels for the L2N gradients (cir_l2n_bwd_rows), the three [N, C] x [C, D]-sized products of the Linear through
+    cuBLAS (plain library GEMMs on 64-row operands), dL/db by cir_colsum_rows, ONE streaming kernel (cir_gem_bwd) for
+    everything that touches the feature map (dx and the sum needed for dL/dp) and cir_gem_dp.  MAC / SPoC recompute the
+    tail with differentiable torch ops."""
 
     @staticmethod
     def forward(ctx, x, p, weight, bias, eps, pooling, flags, l2_eps):
         ctx.cfg = (eps, pooling, flags, l2_eps)
         xc = _as_f32_contig(x)
-        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps)
         g = None
-        if pooling in ("GeM", "GeMmp") and out.shape[0] > 0:
-            N, Cc = xc.shape[0], xc.shape[1]
-            if flags & CIR_TAIL_POOL_ONLY:
-                g = out
-            else:   # the kernel left the pooled values at the head of its workspace: keep a copy (N*C*4 bytes)
-                ws = _lib.workspace(xc.device, 0, "tail")
-                if flags & CIR_TAIL_NO_WHITEN:
-                    g = ws[:N * Cc * 4].view(torch.float32).view(N, Cc).clone()
-                else:   # whitening: stored as bf16 hi + lo parts ([N, C] each), g = hi + lo
-                    hl = ws[:N * Cc * 4].view(torch.bfloat16).view(2, N, Cc)
-                    g = hl[0].float() + hl[1].float()
+        gem_path = pooling in ("GeM", "GeMmp") and xc.shape[0] > 0
+        if gem_path and not (flags & CIR_TAIL_POOL_ONLY):
+            g = torch.empty((xc.shape[0], xc.shape[1]), dtype=torch.float32, device=xc.device)
+        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, pooled_out=g)
+        if gem_path and (flags & CIR_TAIL_POOL_ONLY):
+            g = out
         ctx.save_for_backward(xc, p, weight, bias, g)
         return out
 
@@ -151,27 +160,27 @@ class _TailFn(torch.autograd.Function):
             if flags & CIR_TAIL_POOL_ONLY:
                 dg = gout
             elif flags & CIR_TAIL_NO_WHITEN:
-                dg = _l2n_bwd(g, gout, l2_eps)
+                dg, _ = _l2n_bwd_rows(g, gout, l2_eps)
             else:
-                s = g.norm(p=2, dim=1, keepdim=True)
-                u = g / (s + l2_eps)
-                z = torch.nn.functional.linear(u, weight, bias)
-                dz = _l2n_bwd(z, gout, l2_eps)
+                _, u = _l2n_bwd_rows(g, None, l2_eps, want_unit=True)          # u = g / (||g|| + eps)
+                z = torch.addmm(bias, u, weight.t()) if bias is not None else u @ weight.t()
+                dz, _ = _l2n_bwd_rows(z, gout, l2_eps)
                 if need[2]:
                     dW = dz.t() @ u
                 if bias is not None and need[3]:
-                    db = dz.sum(dim=0)
-                dg = _l2n_bwd(g, dz @ weight, l2_eps)
+                    db = _colsum_rows(dz)
+                dg, _ = _l2n_bwd_rows(g, dz @ weight, l2_eps)
             dx = dp = None
             if need[0] or need[1]:
-                dx, S = _gem_bwd_launch(x, p, eps, g, dg.contiguous(), need[0], need[1])
+                dx, S = _gem_bwd_launch(x, p, eps, g, dg, need[0], need[1])
                 if need[1]:
-                    pp = p.detach().reshape(1, -1).float()
-                    HW = x.shape[2] * x.shape[3]
-                    # d g / d p = g * ( -ln(g) / p + S / (p * HW * g^p) ),  g^p = mean t^p
-                    dgdp = g * (-torch.log(g) / pp + S / (pp * HW * g.pow(pp)))
-                    dp_full = (dg * dgdp)
-                    dp = dp_full.sum().reshape(p.shape) if p.numel() == 1 else dp_full.sum(dim=0).reshape(p.shape)
+                    lib = _lib.load()
+                    pc = p.detach().reshape(-1).float().contiguous()
+                    dp = torch.empty_like(pc)
+                    rc = lib.cir_gem_dp(_lib.ptr(g), _lib.ptr(dg), _lib.ptr(S), _lib.ptr(pc), 0 if pc.numel() == 1 else 1,
+                                        g.shape[0], g.shape[1], x.shape[2] * x.shape[3], _lib.ptr(dp), _lib.stream_of(g))
+                    _lib.check(rc, "cir_gem_dp")
+                    dp = dp.reshape(p.shape)
         return dx, dp, dW, db, None, None, None, None
 
     @staticmethod
@@ -261,44 +270,91 @@ def rmac_regions(H, W, L=3):
     return [(i, j, wl, wl) for (wl, cenH, cenW) in rmac_grid(H, W, L) if wl > 0 for i in cenH for j in cenW]
 
 
-def region_pool(x, regions, p=None, eps=1e-6, pooling="GeM"):
-    """Pool every (row0, col0, height, width) region of an N x C x H x W map in ONE pass over the map
-    (cir_region_pool) -> N x R x C.  ``pooling`` / ``p`` / ``eps`` as in descriptor_tail."""
+def _region_pool_launch(x, regions, p, eps, pooling):
     import ctypes as C
-    if pooling not in _POOL:
-        raise KeyError(pooling)
-    _lib.require_cuda(x, p if torch.is_tensor(p) else None)
     lib = _lib.load()
-    x = _as_f32_contig(x)
-    if x.dim() != 4:
-        raise ValueError("expected an N x C x H x W feature map, got shape %s" % (tuple(x.shape),))
     N, Cc, H, W = x.shape
     R = len(regions)
-    if R < 1:
-        raise ValueError("region_pool needs at least one region")
     p_stride = 0
-    if pooling in ("GeM", "GeMmp"):
-        if p is None:
-            raise ValueError("GeM pooling needs the exponent p")
-        if not torch.is_tensor(p):
-            p = torch.full((1,), float(p), dtype=torch.float32, device=x.device)
+    if p is not None:
         p = p.detach().reshape(-1).float().contiguous()
-        if p.numel() not in (1, Cc):
-            raise ValueError("GeM exponent must have 1 or C=%d elements, got %d" % (Cc, p.numel()))
         p_stride = 0 if p.numel() == 1 else 1
-    else:
-        p = None
-    flat = []
-    for r in regions:
-        if len(r) != 4:
-            raise ValueError("a region is (row0, col0, height, width)")
-        flat.extend(int(v) for v in r)
+    flat = [int(v) for r in regions for v in r]
     reg = (C.c_int32 * len(flat))(*flat)
     out = torch.empty((N, R, Cc), dtype=torch.float32, device=x.device)
     rc = lib.cir_region_pool(_lib.ptr(x), N, Cc, H, W, C.cast(reg, C.c_void_p), R, _lib.ptr(p), p_stride, float(eps),
                              _POOL[pooling], _lib.ptr(out), _lib.stream_of(x))
     _lib.check(rc, "cir_region_pool")
     return out
+
+
+def _region_pool_formula(x, regions, p, eps, pooling):
+    """The same pooling with stock differentiable torch ops (pools.py:126-167 region by region) -- gradients only."""
+    vecs = []
+    for (i, j, h, w) in regions:
+        r = x[:, :, i:i + h, j:j + w]
+        if pooling in ("GeM", "GeMmp"):
+            pp = p.reshape(1, -1, 1, 1) if p.numel() > 1 else p
+            v = r.clamp(min=eps).pow(pp).mean(dim=(-2, -1)).pow(1.0 / p)
+        elif pooling == "MAC":
+            v = r.amax(dim=(-2, -1))
+        else:
+            v = r.mean(dim=(-2, -1))
+        vecs.append(v)
+    return torch.stack(vecs, dim=1)
+
+
+class _RegionPoolFn(torch.autograd.Function):
+    """Forward = cir_region_pool (one pass over the map); backward recomputes the regions with differentiable torch ops."""
+
+    @staticmethod
+    def forward(ctx, x, p, regions, eps, pooling):
+        ctx.cfg = (regions, eps, pooling)
+        ctx.save_for_backward(x, p)
+        return _region_pool_launch(x, regions, p, eps, pooling)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, p = ctx.saved_tensors
+        regions, eps, pooling = ctx.cfg
+        with torch.enable_grad():
+            xl = x.detach().requires_grad_(ctx.needs_input_grad[0])
+            pl = None if p is None else p.detach().requires_grad_(ctx.needs_input_grad[1])
+            ins = [t for t, need in ((xl, ctx.needs_input_grad[0]), (pl, p is not None and ctx.needs_input_grad[1])) if need]
+            grads = torch.autograd.grad(_region_pool_formula(xl, regions, pl, eps, pooling), ins, gout.contiguous()) if ins else ()
+        it = iter(grads)
+        gx = next(it) if ctx.needs_input_grad[0] else None
+        gp = next(it) if (p is not None and ctx.needs_input_grad[1]) else None
+        return gx, gp, None, None, None
+
+
+def region_pool(x, regions, p=None, eps=1e-6, pooling="GeM"):
+    """Pool every (row0, col0, height, width) region of an N x C x H x W map in ONE pass over the map
+    (cir_region_pool) -> N x R x C.  ``pooling`` / ``p`` / ``eps`` as in descriptor_tail.  Differentiable in x and p."""
+    if pooling not in _POOL:
+        raise KeyError(pooling)
+    _lib.require_cuda(x, p if torch.is_tensor(p) else None)
+    if x.dim() != 4:
+        raise ValueError("expected an N x C x H x W feature map, got shape %s" % (tuple(x.shape),))
+    Cc = x.shape[1]
+    if len(regions) < 1:
+        raise ValueError("region_pool needs at least one region")
+    for r in regions:
+        if len(r) != 4:
+            raise ValueError("a region is (row0, col0, height, width)")
+    if pooling in ("GeM", "GeMmp"):
+        if p is None:
+            raise ValueError("GeM pooling needs the exponent p")
+        if not torch.is_tensor(p):
+            p = torch.full((1,), float(p), dtype=torch.float32, device=x.device)
+        if p.numel() not in (1, Cc):
+            raise ValueError("GeM exponent must have 1 or C=%d elements, got %d" % (Cc, p.numel()))
+    else:
+        p = None
+    regions = [tuple(int(v) for v in r) for r in regions]
+    if torch.is_grad_enabled() and (x.requires_grad or (p is not None and p.requires_grad)):
+        return _RegionPoolFn.apply(_as_f32_contig(x), p, regions, eps, pooling)
+    return _region_pool_launch(_as_f32_contig(x), regions, p, eps, pooling)
 
 
 def gem(x, p=3, eps=1e-6):
@@ -362,12 +418,35 @@ def l2n(x, eps=1e-6):
     return y.reshape(moved.shape).movedim(-1, 1)
 
 
-def powerlaw(x, eps=1e-6):
-    """sign(x + eps) * sqrt(|x + eps|), cirtorch/modules/normalizations.py:25-27 (inference only)."""
-    _lib.require_cuda(x)
+def _powerlaw_launch(x, eps):
     lib = _lib.load()
     xc = _as_f32_contig(x)
     out = torch.empty_like(xc)
     rc = lib.cir_powerlaw(_lib.ptr(xc), xc.numel(), float(eps), _lib.ptr(out), _lib.stream_of(xc))
     _lib.check(rc, "cir_powerlaw")
     return out
+
+
+class _PowerLawFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        ctx.eps = eps
+        ctx.save_for_backward(x)
+        return _powerlaw_launch(x, eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        with torch.enable_grad():
+            x2 = x.detach().requires_grad_(True)
+            t = x2 + ctx.eps
+            (gx,) = torch.autograd.grad(t.abs().sqrt().mul(t.sign()), x2, g)       # normalizations.py:25-27
+        return gx, None
+
+
+def powerlaw(x, eps=1e-6):
+    """sign(x + eps) * sqrt(|x + eps|), cirtorch/modules/normalizations.py:25-27.  Differentiable in x."""
+    _lib.require_cuda(x)
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _PowerLawFn.apply(x, eps)
+    return _powerlaw_launch(x, eps)

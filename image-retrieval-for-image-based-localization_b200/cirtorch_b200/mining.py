@@ -34,10 +34,33 @@ def mine_filter(cand, pool_cluster, q_cluster, nnum, q_rows=None, pool_rows=None
     return sel, cnt, dist
 
 
+TOL = {"bf16x3": 2e-5, "bf16": 5e-4}      # |scan score - fp32 score| on unit-norm descriptors
+
+
+def _full_ranking_fp32(sub_q, pool_rows):
+    """Exact fp32 full ranking of a few straggler queries: bf16x3 dense scores order the pool, every 4096-entry window
+    of that order is re-scored exactly in fp32 (cir_rescore_topk), the exact scores are scattered back into a dense
+    [Q, P] matrix and sorted (torch.sort of the reference, tuples_dataset.py:319)."""
+    dense = S.scores_dense_rows(sub_q, pool_rows, mode="bf16x3")
+    order = S.argsort_rows_desc(dense)
+    P = pool_rows.shape[0]
+    for a in range(0, P, 4096):
+        b = min(P, a + 4096)
+        sc, ix = S.rescore_rows(sub_q, pool_rows, order[:, a:b], b - a)
+        dense.scatter_(1, ix.long(), sc)
+    return S.argsort_rows_desc(dense)
+
+
 def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num, mode="bf16x3", kc=None):
     """Device-level mining.  q_rows [Q, D], pool_rows [P, D] fp32; *_cluster int32 device tensors.
 
-    Returns (sel [Q, neg_num] int32 pool positions best-first, dist [Q, neg_num] = ||q - n + 1e-6||_2).
+    Returns (sel [Q, neg_num] int32 pool positions best-first, count [Q], dist [Q, neg_num] = ||q - n + 1e-6||_2).
+
+    Exactness.  The candidates of a query are its kc best pool rows by the bf16x3 scan (own cluster masked), re-ordered by
+    exact fp32 scores.  The walk over them is conclusive only if (a) it found neg_num negatives and (b) the fp32 score of
+    the LAST negative taken clears the scan score of the kc-th candidate by 2 * TOL[mode] -- otherwise a row just outside
+    the list could outrank the walk's tail -- or the list already holds every row the query may take.  Anything else is
+    re-run with a 4x longer list and finally with an exact fp32 full ranking.
     """
     S._check_rows(q_rows)
     S._check_rows(pool_rows)
@@ -49,30 +72,32 @@ def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num
     qp = S.pack_rows(q_rows, "query", mode)
     pp = S.pack_rows(pool_rows, "db", mode)
     sel = cnt = dist = None
-    todo = None               # indices of queries still short of neg_num
+    todo = None               # indices of queries still open
     while True:
         sub_q = q_rows if todo is None else q_rows[todo].contiguous()
         sub_qp = qp if todo is None else qp[todo].contiguous()
         sub_qc = q_cluster if todo is None else q_cluster[todo].contiguous()
         kk = min(kc, S.MAX_K)
-        _, cand = S.search_packed(sub_qp, pp, kk, q_label=sub_qc, db_label=pool_cluster)
+        s3, cand = S.search_packed(sub_qp, pp, kk, q_label=sub_qc, db_label=pool_cluster)
         _, cand = S.rescore_rows(sub_q, pool_rows, cand, kk)          # exact fp32 order
         s2, c2, d2 = mine_filter(cand, pool_cluster, sub_qc, neg_num, sub_q, pool_rows)
+        # margin of the last negative taken over the first row that did NOT make the list
+        last = pool_rows[s2[:, neg_num - 1].clamp_min(0).long()]
+        t_last = (sub_q * last).sum(dim=1)
+        complete = torch.isinf(s3[:, kk - 1])                          # fewer than kk rows qualify: nothing is outside the list
+        open_ = ~complete & ((c2 < neg_num) | (t_last - s3[:, kk - 1] < 2 * TOL[mode]))
         if todo is None:
             sel, cnt, dist = s2, c2, d2
         else:
             sel[todo], cnt[todo], dist[todo] = s2, c2, d2
-        # a list is conclusive if it found neg_num negatives or already covers the whole pool
-        short = (cnt < neg_num)
-        if kk >= P or not bool(short.any()):
+        if kk >= P or not bool(open_.any()):
             break
-        todo = torch.nonzero(short).flatten()
+        todo = torch.nonzero(open_).flatten() if todo is None else todo[torch.nonzero(open_).flatten()]
         if kc >= S.MAX_K:
-            # full ranking for the stragglers: dense scores + full sort, then the same walk
+            # exact full ranking for the stragglers, then the same walk
             sub_q = q_rows[todo].contiguous()
             sub_qc = q_cluster[todo].contiguous()
-            dense = S.scores_dense_rows(sub_q, pool_rows, mode="bf16x3")
-            order = S.argsort_rows_desc(dense)
+            order = _full_ranking_fp32(sub_q, pool_rows)
             s2, c2, d2 = mine_filter(order, pool_cluster, sub_qc, neg_num, sub_q, pool_rows)
             sel[todo], cnt[todo], dist[todo] = s2, c2, d2
             break
@@ -86,7 +111,7 @@ def mine_hard_negatives(qvecs, poolvecs, clusters, query_indices, idxs2images, n
     qvecs D x Q, poolvecs D x P (CUDA fp32, descriptors as columns); ``clusters[i]`` = cluster id of
     dataset image i; ``query_indices[q]`` = dataset index of query q; ``idxs2images[j]`` = dataset
     index of pool entry j.  Returns (negative_indices: list of Q lists of ``neg_num`` dataset
-    indices, average negative L2 distance) exactly like the reference's ``self.nidxs`` / return value.
+    indices, average negative L2 distance) exactly like the reference's ``self.negative_indices`` / return value.
     """
     dev = qvecs.device
     clusters_t = torch.as_tensor(np.asarray(clusters), dtype=torch.int64)
@@ -106,29 +131,93 @@ def mine_hard_negatives(qvecs, poolvecs, clusters, query_indices, idxs2images, n
 
 
 class TuplesMiner:
-    """Host-side state of the reference's TuplesDataset that mining touches (tuples_dataset.py:50-103):
-    ``clusters`` per image, the query / positive pools, epoch sizes; ``create_epoch_tuples`` re-draws
-    the epoch's queries and negative pool (:223-229) and mines ``nnum`` negatives per query."""
+    """Host-side state of the reference's ``TuplesDataset`` that mining touches (tuples_dataset.py:50-103), with its
+    attribute names: ``clusters`` per image, ``query_pool`` / ``positive_pool``, ``neg_num``, ``query_size``,
+    ``pool_size``; after :meth:`create_epoch_tuples`: ``query_indices``, ``positive_indices``, ``negative_indices``.
 
-    def __init__(self, clusters, qpool, ppool, nnum=5, qsize=2000, poolsize=20000):
+    ``images``: what the epoch's descriptors are extracted from -- a sequence of 3 x H x W tensors (or image paths,
+    loaded with PIL) indexed like ``clusters``; or pass ``extract_fn`` to :meth:`create_epoch_tuples`."""
+
+    def __init__(self, clusters, query_pool, positive_pool, neg_num=5, query_size=2000, pool_size=20000, images=None,
+                 transform=None, name="retrieval-SfM-120k", mode="train", *, nnum=None, qsize=None, poolsize=None):
+        self.name, self.mode = name, mode
         self.clusters = np.asarray(clusters)
-        self.qpool = np.asarray(qpool)
-        self.ppool = np.asarray(ppool)
-        self.nnum = nnum
-        self.qsize = min(qsize, len(self.qpool))
-        self.poolsize = min(poolsize, len(self.clusters))
-        self.qidxs = self.pidxs = self.nidxs = None
+        self.query_pool = np.asarray(query_pool)
+        self.positive_pool = np.asarray(positive_pool)
+        self.images = images
+        self.transform = transform
+        self.neg_num = neg_num if nnum is None else nnum
+        self.query_size = min(query_size if qsize is None else qsize, len(self.query_pool))
+        self.pool_size = min(pool_size if poolsize is None else poolsize, len(self.clusters))
+        self.query_indices = self.positive_indices = self.negative_indices = None
 
-    def create_epoch_tuples(self, extract_fn, generator=None):
-        """``extract_fn(image_indices) -> D x n CUDA descriptors`` (e.g. a closure over extract_vectors)."""
-        idxs2qpool = torch.randperm(len(self.qpool), generator=generator)[:self.qsize]
-        self.qidxs = [int(self.qpool[i]) for i in idxs2qpool]
-        self.pidxs = [int(self.ppool[i]) for i in idxs2qpool]
-        if self.nnum == 0:
-            self.nidxs = [[] for _ in self.qidxs]
+    # upstream cnnimageretrieval-pytorch names of the same lists
+    qidxs = property(lambda self: self.query_indices)
+    pidxs = property(lambda self: self.positive_indices)
+    nidxs = property(lambda self: self.negative_indices)
+
+    def _load(self, i):
+        item = self.images[i]
+        if not torch.is_tensor(item):
+            from PIL import Image
+            with Image.open(item) as im:
+                item = im.convert("RGB")
+        return self.transform(item) if self.transform is not None else item
+
+    def _extract(self, model, indices, output_dim, batch_size, device, rank, world_size):
+        """The extraction loops of tuples_dataset.py:259-272 / :300-312: descriptors as columns of zeros(D, n); rank r of
+        ``world_size`` fills the batches it owns (the reference's distributed sampler) and the parts are summed."""
+        from .utils.sequence import PackedSequence
+        vecs = torch.zeros(output_dim, len(indices), device=device)
+        for b, a in enumerate(range(0, len(indices), batch_size)):
+            if b % world_size != rank:
+                continue
+            batch = [self._load(i).to(device, non_blocking=True) for i in indices[a:a + batch_size]]
+            out = model(img=PackedSequence(batch), do_prediction=True)
+            pred = out[1]["ret_pred"] if isinstance(out, tuple) else out
+            vecs[:, a:a + len(batch)] = pred
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(vecs)
+        return vecs
+
+    def create_epoch_tuples(self, model, log_info=None, log_debug=None, *, extract_fn=None, generator=None, **varargs):
+        """tuples_dataset.py:213-350 with its call shape ``(model, log_info, log_debug, output_dim=, world_size=, rank=,
+        device=, data_config=)``: draws the epoch's (query, positive) pairs and the negative pool, extracts their
+        descriptors with ``model`` (``model(img=PackedSequence, do_prediction=True)`` -> ``(_, {"ret_pred": D x B})``),
+        mines ``neg_num`` hard negatives per query on the device, sets ``self.negative_indices``, logs and returns the
+        average negative L2 distance.
+
+        ``extract_fn(image_indices) -> D x n CUDA descriptors`` replaces the extraction (descriptors already in HBM)."""
+        log_info = log_info or (lambda *a: None)
+        log_debug = log_debug or (lambda *a: None)
+        log_debug('Creating tuples for an epoch of {%s}--{%s}', self.name, self.mode)
+        if hasattr(model, "eval"):
+            model.eval()
+        idxs2qpool = torch.randperm(len(self.query_pool), generator=generator)[:self.query_size]
+        self.query_indices = [int(self.query_pool[i]) for i in idxs2qpool]
+        self.positive_indices = [int(self.positive_pool[i]) for i in idxs2qpool]
+        if self.neg_num == 0:
+            self.negative_indices = [[] for _ in self.query_indices]
             return 0.0
-        idxs2images = torch.randperm(len(self.clusters), generator=generator)[:self.poolsize]
-        qvecs = extract_fn(self.qidxs)
-        poolvecs = extract_fn(idxs2images.tolist())
-        self.nidxs, avg = mine_hard_negatives(qvecs, poolvecs, self.clusters, self.qidxs, idxs2images, self.nnum)
+        idxs2images = torch.randperm(len(self.clusters), generator=generator)[:self.pool_size]
+        with torch.no_grad():
+            if extract_fn is not None:
+                qvecs = extract_fn(self.query_indices)
+                poolvecs = extract_fn(idxs2images.tolist())
+            else:
+                if self.images is None:
+                    raise ValueError("TuplesMiner needs images= (or extract_fn=) to extract the epoch's descriptors")
+                cfg = varargs.get("data_config")
+                batch_size = (cfg.getint("test_batch_size") * 2) if cfg is not None else varargs.get("batch_size", 16)
+                device = varargs.get("device") or next(model.parameters()).device
+                args = (varargs["output_dim"], batch_size, device, varargs.get("rank", 0), varargs.get("world_size", 1))
+                log_debug('Extracting descriptors for query images :')
+                qvecs = self._extract(model, self.query_indices, *args)
+                log_debug('Extracting descriptors for negative pool :')
+                poolvecs = self._extract(model, idxs2images.tolist(), *args)
+            log_debug('Searching for hard negatives :')
+            self.negative_indices, avg = mine_hard_negatives(qvecs, poolvecs, self.clusters, self.query_indices, idxs2images,
+                                                             self.neg_num)
+        log_info('Average negative l2-distance = %f', avg)
         return avg

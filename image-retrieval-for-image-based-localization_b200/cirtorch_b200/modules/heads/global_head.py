@@ -36,6 +36,16 @@ class globalHead(nn.Module):
     def forward(self, x, do_whitening=True, *, out=None, accumulate=False):
         """``out`` / ``accumulate`` (extensions, inference only): write the descriptors into / add them to an existing
         D x N result of this head -- the running sum of the multi-scale mean (GF_net.py:74-92)."""
+        from ..normalizations import L2N
+        if not isinstance(self.norm, L2N):
+            # any other registered normalisation (PowerLaw): the reference's composition pool -> norm -> whiten -> norm
+            # (global_head.py:57-64) layer by layer; only L2N is fused into the tail kernel
+            if out is not None or accumulate:
+                raise ValueError("out= / accumulate= need the fused L2N tail")
+            v = self.norm(self.pool(x)).squeeze(-1).squeeze(-1)
+            if do_whitening:
+                v = self.norm(self.whiten(v))
+            return v.permute(1, 0)
         phys = None if out is None else out.permute(1, 0)          # the physical N x D buffer behind a D x N result
         kw = dict(weight=self.whiten.weight, bias=self.whiten.bias, do_whitening=do_whitening, l2_eps=self.norm.eps,
                   out=phys, accumulate=accumulate)

@@ -124,7 +124,9 @@ class Rpool(nn.Module):
         o = self.roipool(x)
         N, R, C = o.shape[:3]
         o = o.reshape(N * R, C)
-        if isinstance(self.whiten, nn.Linear) and not (torch.is_grad_enabled() and self.whiten.weight.requires_grad):
+        needs_grad = torch.is_grad_enabled() and (o.requires_grad or (isinstance(self.whiten, nn.Linear) and any(
+            t.requires_grad for t in self.whiten.parameters())))
+        if isinstance(self.whiten, nn.Linear) and not needs_grad:
             # L2N -> Linear -> L2N of the N*R region vectors: row L2N, the tcgen05 GEMM in bf16x3 mode (~fp32 accurate,
             # the path whitenapply takes) and the fused bias + L2N kernel
             from .. import _lib, search as _search

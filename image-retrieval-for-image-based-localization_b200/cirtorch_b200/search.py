@@ -132,6 +132,10 @@ def search_topk_rows(q_rows, db_rows, k, mode="bf16", rescore=None, db_packed=No
         _check_rows(db_rows)
     if rescore is None:
         rescore = mode == "bf16" and db_rows is not None
+    if rescore and db_rows is None:
+        raise ValueError("rescore=True needs the fp32 database rows (db_rows); this index keeps only the packed operand")
+    if db_rows is None and db_packed is None:
+        raise ValueError("search_topk_rows needs db_rows or db_packed")
     qp = pack_rows(q_rows, "query", mode)
     dbp = db_packed if db_packed is not None else pack_rows(db_rows, "db", mode)
     if not rescore or q_rows.shape[0] == 0 or dbp.shape[0] == 0:

@@ -70,9 +70,10 @@ def load_training_db(db_fn, mode="train"):
     return {"cids": db["cids"], "cluster": db["cluster"], "qidxs": db["qidxs"], "pidxs": db["pidxs"]}
 
 
-def miner_from_training_db(db, nnum=5, qsize=2000, poolsize=20000):
+def miner_from_training_db(db, nnum=5, qsize=2000, poolsize=20000, images=None, transform=None):
     from .mining import TuplesMiner
-    return TuplesMiner(db["cluster"], db["qidxs"], db["pidxs"], nnum=nnum, qsize=qsize, poolsize=poolsize)
+    return TuplesMiner(db["cluster"], db["qidxs"], db["pidxs"], neg_num=nnum, query_size=qsize, pool_size=poolsize,
+                       images=images, transform=transform)
 
 
 def load_ret_head(snapshot_file, head, strict_shapes=False):

@@ -68,6 +68,7 @@ struct TailParams {
     int pooled_ld;
     __nv_bfloat16* pooled_hi;   // whiten mode: pooled vectors as bf16 hi + lo parts, [N, C] each (same bytes as fp32)
     __nv_bfloat16* pooled_lo;
+    float* pooled_out; // optional caller-owned [N, C] fp32 copy of the pooled values (kept for the backward pass)
     float* part;       // [n_kslices][N][D_out] partial projections of the K slices
     int n_ntiles, n_kslices, units;   // projection units: u = ks * n_ntiles + nt
     unsigned flags;
@@ -352,6 +353,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                 const long long n = held_row / P.C;
                 const float pl = gem ? __ldg(P.p + c * P.p_stride) : 1.0f;
                 const float v = finish_row(classify_p(P.pool_mode, pl), held, HW, pl);
+                if (P.pooled_out) P.pooled_out[n * P.C + c] = v;
                 if (P.pooled_hi) {
                     // the projection consumes bf16 hi + lo operands: split once here instead of in all 148 CTAs
                     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -723,7 +725,7 @@ extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) 
 
 extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const float* p, int p_stride,
                             float eps_gem, float eps_l2, int pool_mode, const float* Wt,
-                            const float* bias, int D_out, float* out, int out_ld, void* workspace,
+                            const float* bias, int D_out, float* out, int out_ld, float* pooled_out, void* workspace,
                             size_t workspace_bytes, unsigned flags, void* stream) {
     CIR_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0, CIR_ERR_INVALID_ARG,
                 "cir_tail_fwd: null pointer or empty shape (N=%d C=%d H=%d W=%d)", N, C, H, W);
@@ -744,6 +746,7 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.x = x; P.N = N; P.C = C; P.HW = H * W;
     P.p = p; P.p_stride = p_stride; P.eps_gem = eps_gem; P.eps_l2 = eps_l2; P.pool_mode = pool_mode;
     P.Wt = Wt; P.bias = bias; P.D_out = D_out; P.out = out; P.out_ld = out_ld; P.flags = flags;
+    P.pooled_out = pool_only ? nullptr : pooled_out;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
     {

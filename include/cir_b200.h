@@ -73,6 +73,8 @@ int64_t cir_launch_count(int reset);
  *             CIR_TAIL_NO_WHITEN / CIR_TAIL_POOL_ONLY (then D_out must equal C)
  *    bias     device, [D_out] or NULL (= zeros)
  *    out      device, [N, out_ld] fp32, out_ld >= D_out
+ *    pooled_out  optional device [N, C] fp32: the pooled values (before the first L2N), which the backward pass
+ *             needs (cir_gem_bwd); NULL = not wanted
  *    One cooperative launch: phase A streams x once (HBM-bound), a grid barrier, phase B
  *    does the projection from L2-resident pooled vectors, a second barrier, final L2N.
  * ------------------------------------------------------------------------------------ */
@@ -80,7 +82,7 @@ int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes);
 int cir_tail_fwd(const float* x, int N, int C, int H, int W,
                  const float* p, int p_stride, float eps_gem, float eps_l2, int pool_mode,
                  const float* Wt, const float* bias, int D_out,
-                 float* out, int out_ld,
+                 float* out, int out_ld, float* pooled_out,
                  void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
 /* Backward of the GeM pooling over the feature map (training, scripts/train_globalF.py:480-488; the autograd of
@@ -228,6 +230,35 @@ int cir_eval_ap(const int32_t* ranks, int Q, int64_t R, int64_t ld,
                 const int32_t* ok_off, const int32_t* ok_idx,
                 const int32_t* junk_off, const int32_t* junk_idx,
                 const int32_t* kappas, int nk, double* ap_out, double* prs_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 7. Training side of the head
+ *    cir_tuple_loss replaces contrastive_loss / triplet_loss   cirtorch/modules/losses.py:7-23 / :26-46
+ *    (called through globalFeatureLoss, cirtorch/algos/GF_algo.py:11-34,64-83) on the descriptors of
+ *    n_tuples training tuples (query, positive, negatives): x [n_tuples * S, ldx] fp32 rows (the physical
+ *    layout behind the reference's D x N tensor), label [n_tuples * S] int32 with -1 = query, 1 = positive,
+ *    0 = negative.  ONE launch computes loss[0] (the sum over all pairs / triplets) and, when grad != NULL,
+ *    d loss / d x into grad [n_tuples * S, ldg].  contrastive: the query is the FIRST row of a tuple
+ *    (x[:, ::S], losses.py:13), eps is added to the difference (:20); triplet: squared distances, one
+ *    positive per tuple (:38-44).  Deterministic (fixed-order reductions).
+ * ------------------------------------------------------------------------------------ */
+#define CIR_LOSS_CONTRASTIVE 0
+#define CIR_LOSS_TRIPLET 1
+int cir_tuple_loss_workspace_bytes(int n_tuples, size_t* bytes);
+int cir_tuple_loss(const float* x, int64_t ldx, int n_tuples, int S, int D, const int32_t* label, int kind,
+                   float margin, float eps, float* loss, float* grad, int64_t ldg,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the [N, C]-sized part of globalHead.forward (global_head.py:57-64), the pieces between the cuBLAS-sized
+ * products:  cir_l2n_bwd_rows: out = d/dv [ v / (||v|| + eps) ] applied to gout, per row; unit_out (optional) = the
+ * forward value v / (||v|| + eps); gout / out may be NULL when only unit_out is wanted.  cir_colsum_rows: out[c] =
+ * sum_n X[n, c] (dL/db).  cir_gem_dp: dL/dp of GeM (pools.py:37-38) from the pooled values g, their gradient dg and
+ * S = sum t^p ln t of cir_gem_bwd: out[0] (p_stride 0) or out[c] (p_stride 1). */
+int cir_l2n_bwd_rows(const float* v, const float* gout, int64_t N, int C, float eps, float* out, float* unit_out,
+                     void* stream);
+int cir_colsum_rows(const float* X, int64_t N, int C, float* out, void* stream);
+int cir_gem_dp(const float* g, const float* dg, const float* S, const float* p, int p_stride, int N, int C, int HW,
+               float* out, void* stream);
 
 #ifdef __cplusplus
 }

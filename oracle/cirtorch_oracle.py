@@ -16,6 +16,9 @@ Parity status
   * tail (GeM / MAC / SPoC / L2N / globalHead), regional pooling (Rpool / RMAC), whitenapply / whitenlearn /
     pcawhitenlearn / cholesky, compute_ap / compute_map, multi-scale mean:
     PINNED by fixtures generated from the imported reference code.
+  * contrastive_loss / triplet_loss (cirtorch/modules/losses.py:7-46) and the padded-batch forward of
+    ImageRetrievalNet + globalFeatureAlgo (cirtorch/models/GF_net.py:94-126, cirtorch/algos/GF_algo.py:51-94):
+    PINNED by fixtures generated from the imported reference code (losses.npz, net.npz).
   * ranking (scripts/train_globalF.py:733-734) and hard-negative mining
     (cirtorch/datasets/globalFeatures/tuples_dataset.py:317-350): the reference inlines
     them in a driver / a dataset method that cannot be called standalone; the fixture
@@ -395,3 +398,68 @@ def compute_map_revisited(ranks, gnd, kappas=(1, 5, 10)):
     m = compute_map(ranks, regroup(["easy", "hard"], ["junk"]), kappas)
     h = compute_map(ranks, regroup(["hard"], ["junk", "easy"]), kappas)
     return {"mAP": 100.0 * (m[0] + h[0]) / 2.0, "E": e, "M": m, "H": h}
+
+
+# --------------------------------------------------------------------------------------
+# Tuple losses (training side of the head) and the padded-batch forward of the network
+# --------------------------------------------------------------------------------------
+
+
+def contrastive_loss(x: torch.Tensor, label: torch.Tensor, margin: float = 0.7, eps: float = 1e-6) -> torch.Tensor:
+    """cirtorch/modules/losses.py:7-23.  x: D x N columns, a tuple = S consecutive columns starting with its query
+    (label -1); every other column j of the tuple pairs with the query:
+    d = ||x_q - x_j + eps||, y = 0.5 l d^2 + 0.5 (1 - l) max(margin - d, 0)^2, summed."""
+    nq = int((label == -1).sum())
+    S = x.shape[1] // nq
+    total = x.new_zeros(())
+    for t in range(nq):
+        xq = x[:, t * S]
+        for j in range(t * S, (t + 1) * S):
+            if label[j] == -1:
+                continue
+            d = ((xq - x[:, j] + eps) ** 2).sum().sqrt()
+            l = label[j].to(x.dtype)
+            total = total + 0.5 * l * d ** 2 + 0.5 * (1 - l) * torch.clamp(margin - d, min=0) ** 2
+    return total
+
+
+def triplet_loss(x: torch.Tensor, label: torch.Tensor, label_msk: torch.Tensor, margin: float = 0.1) -> torch.Tensor:
+    """cirtorch/modules/losses.py:26-46.  Per tuple: anchor (label -1), positive (1), negatives (0);
+    sum over negatives of max(|a - p|^2 - |a - n|^2 + margin, 0)."""
+    nt = len(torch.unique(label_msk))
+    S = x.shape[1] // nt
+    total = x.new_zeros(())
+    for t in range(nt):
+        cols = range(t * S, (t + 1) * S)
+        a = x[:, [j for j in cols if label[j] == -1][0]]
+        p = x[:, [j for j in cols if label[j] == 1][0]]
+        dp = ((a - p) ** 2).sum()
+        for j in cols:
+            if label[j] == 0:
+                total = total + torch.clamp(dp - ((a - x[:, j]) ** 2).sum() + margin, min=0.0)
+    return total
+
+
+def pad_images(images, pad_value: float = 0.0) -> torch.Tensor:
+    """cirtorch/utils/sequence.py:4-58: ragged C x H x W images, top-left aligned in one N x C x Hmax x Wmax tensor."""
+    H = max(t.shape[-2] for t in images)
+    W = max(t.shape[-1] for t in images)
+    out = images[0].new_full((len(images), images[0].shape[0], H, W), pad_value)
+    for i, t in enumerate(images):
+        out[i, :, :t.shape[-2], :t.shape[-1]] = t
+    return out
+
+
+def net_forward(body, images, p, eps, weight, bias, scales=(1,)) -> torch.Tensor:
+    """ImageRetrievalNet.forward for inference (cirtorch/models/GF_net.py:63-126 with GF_algo.py:85-94): per scale the
+    (rescaled) ragged images are zero-padded to one batch, run through the body, the "mod5" map goes through the head --
+    pooling INCLUDES the padded area (the valid sizes are ignored, GF_algo.py:85-90); scales are averaged without
+    re-normalisation (GF_net.py:74-92).  -> D x B."""
+    preds = []
+    for s in scales:
+        ims = images if s == 1 else [torch.nn.functional.interpolate(t[None], scale_factor=s, mode="bilinear",
+                                                                     align_corners=False)[0] for t in images]
+        fmap = body(pad_images(ims))
+        fmap = fmap["mod5"] if isinstance(fmap, dict) else fmap
+        preds.append(head_forward(fmap, p, eps, weight, bias))
+    return torch.stack(preds, 0).mean(0)

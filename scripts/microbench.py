@@ -73,7 +73,7 @@ if what in ("all", "tail", "stamps"):
     ws = torch.zeros(need.value, dtype=torch.uint8, device=dev)
     for it in range(3):
         rc = lib.cir_tail_fwd(_lib.ptr(x), B, Cc, H, W, _lib.ptr(p3), 0, 1e-6, 1e-6, 0, _lib.ptr(Wt), _lib.ptr(b), 2048,
-                              _lib.ptr(out), 2048, _lib.ptr(ws), ws.numel(), 0x80000000, None)
+                              _lib.ptr(out), 2048, None, _lib.ptr(ws), ws.numel(), 0x80000000, None)
         assert rc == 0
         torch.cuda.synchronize()
     st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :8].cpu().double()
@@ -206,7 +206,7 @@ if what == "smid":
     for it in range(8):
         x = xs[it & 1]
         rc = lib.cir_tail_fwd(_lib.ptr(x), B, Cc, H, W, _lib.ptr(p3), 0, 1e-6, 1e-6, 0, _lib.ptr(Wt), _lib.ptr(b), 2048,
-                              _lib.ptr(out), 2048, _lib.ptr(ws), ws.numel(), 0x80000000, None)
+                              _lib.ptr(out), 2048, None, _lib.ptr(ws), ws.numel(), 0x80000000, None)
         assert rc == 0
         torch.cuda.synchronize()
         st = ws[need.value - 65536:].view(torch.int64).view(-1, 8)[:148, :8].cpu().double()

@@ -80,7 +80,9 @@ def whiten_fixtures():
     m, P = whitenlearn(X, qidxs, pidxs)
     mp, Pp = pcawhitenlearn(X)
     S = np.cov(rs.randn(6, 40))
-    out = dict(X=X, qidxs=qidxs, pidxs=pidxs, m=m, P=P, m_pca=mp, P_pca=Pp,
+    df = X[:, qidxs] - X[:, pidxs]                     # whiten.py:36-37, the fp32 covariance whitenlearn factorises
+    S_lw = np.dot(df, df.T) / df.shape[1]
+    out = dict(X=X, qidxs=qidxs, pidxs=pidxs, m=m, P=P, m_pca=mp, P_pca=Pp, S_lw=S_lw,
                apply=whitenapply(X, m, P), apply_16=whitenapply(X, m, P, dimensions=16),
                apply_pca=whitenapply(X, mp, Pp), S=S, L=cholesky(S))
     np.savez_compressed(os.path.join(OUT, "whiten.npz"), **out)
@@ -222,12 +224,93 @@ def regional_fixtures():
     np.savez_compressed(os.path.join(OUT, "regional.npz"), **cases)
 
 
+def losses_fixtures():
+    """contrastive_loss / triplet_loss (cirtorch/modules/losses.py:7-46) on tuple descriptors, with autograd gradients."""
+    from cirtorch.modules.losses import contrastive_loss, triplet_loss
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for name, (D, nt, nneg) in {"a": (32, 3, 2), "b": (128, 5, 5), "c": (8, 1, 1)}.items():
+        S = 2 + nneg
+        x = torch.randn(D, nt * S, generator=g)
+        x = (x / x.norm(dim=0, keepdim=True)).requires_grad_(True)
+        label = torch.tensor(([-1, 1] + [0] * nneg) * nt, dtype=torch.float32)
+        msk = torch.arange(nt).repeat_interleave(S)
+        out[f"{name}_x"] = x.detach().numpy().copy()
+        out[f"{name}_label"] = label.numpy()
+        out[f"{name}_msk"] = msk.numpy()
+        for margin in (0.7, 0.1):
+            y = contrastive_loss(x, label=label, margin=margin, eps=1e-6)
+            (gx,) = torch.autograd.grad(y, x)
+            out[f"{name}_contrastive_{margin}"] = y.detach().numpy()
+            out[f"{name}_contrastive_{margin}_grad"] = gx.numpy()
+            y = triplet_loss(x, label=label, label_msk=msk, margin=margin)
+            (gx,) = torch.autograd.grad(y, x)
+            out[f"{name}_triplet_{margin}"] = y.detach().numpy()
+            out[f"{name}_triplet_{margin}_grad"] = gx.numpy()
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+
+
+def net_fixtures():
+    """The reference's own ImageRetrievalNet (cirtorch/models/GF_net.py:10-126, augment=None) around its globalFeatureAlgo
+    (cirtorch/algos/GF_algo.py) and globalHead, on a ragged PackedSequence: single- and multi-scale inference and a
+    training step with the triplet loss.  The body is a one-layer stand-in backbone returning {"mod5": map}."""
+    from cirtorch.models.GF_net import ImageRetrievalNet
+    from cirtorch.algos.GF_algo import globalFeatureAlgo, globalFeatureLoss
+    from cirtorch.modules.heads.global_head import globalHead
+    from cirtorch.utils.parallel import PackedSequence
+
+    class Body(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 32, 3, stride=2, padding=1)
+
+        def forward(self, img):
+            return {"mod5": torch.relu(self.conv(img))}
+
+    torch.manual_seed(21)
+    body = Body()
+    head = globalHead(pooling={"name": "GeM", "params": {"p": 2.5, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=32)
+    with torch.no_grad():
+        head.whiten.bias.normal_(0, 0.05)
+    net = ImageRetrievalNet(body, globalFeatureAlgo(globalFeatureLoss("triplet", 0.5), min_level=2, fpn_levels=1), head,
+                            augment=None).eval()
+    g = torch.Generator().manual_seed(22)
+    sizes = [(40, 32), (36, 48), (40, 48), (24, 24)]
+    imgs = [torch.randn(3, h, w, generator=g) for (h, w) in sizes]
+    out = {"conv_w": body.conv.weight.detach().numpy().copy(), "conv_b": body.conv.bias.detach().numpy().copy(),
+           "W": head.whiten.weight.detach().numpy().copy(), "b": head.whiten.bias.detach().numpy().copy(), "p": np.float32(2.5)}
+    for i, t in enumerate(imgs):
+        out[f"img{i}"] = t.numpy()
+    with torch.no_grad():
+        _, pred = net(img=PackedSequence(imgs), scales=[1], do_prediction=True)
+        out["pred"] = pred["ret_pred"].contiguous().numpy()
+        _, pred = net(img=PackedSequence(imgs), scales=[1, 2 ** -0.5, 0.5], do_prediction=True)
+        out["pred_ms"] = pred["ret_pred"].contiguous().numpy()
+    # a training step: 2 tuples (query, positive, 2 negatives), all images of one size
+    timgs = [torch.randn(3, 32, 32, generator=g) for _ in range(8)]
+    for i, t in enumerate(timgs):
+        out[f"timg{i}"] = t.numpy()
+    q, p_, negs = [timgs[0], timgs[4]], [timgs[1], timgs[5]], [[timgs[2], timgs[3]], [timgs[6], timgs[7]]]
+    labels = [torch.tensor([-1., 1., 0., 0.]), torch.tensor([-1., 1., 0., 0.])]
+    net.train()
+    loss, pred = net(img=q, positive_img=p_, negative_img=negs, do_loss=True, do_prediction=False, tuple_labels=labels)
+    loss["ret_loss"].backward()
+    out["train_loss"] = loss["ret_loss"].detach().numpy()
+    out["train_pred"] = pred["ret_pred"].detach().contiguous().numpy()
+    out["train_grad_W"] = head.whiten.weight.grad.numpy().copy()
+    out["train_grad_b"] = head.whiten.bias.grad.numpy().copy()
+    out["train_grad_p"] = head.pool.p.grad.numpy().copy()
+    out["train_grad_conv_w"] = body.conv.weight.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
+
+
 if __name__ == "__main__":
     _import_reference()
     torch.set_num_threads(1)
     only = sys.argv[1:]            # e.g. ``make_golden.py regional`` regenerates one fixture file
     for name, fn in (("tail", tail_fixtures), ("whiten", whiten_fixtures), ("rank", rank_fixtures), ("mining", mining_fixtures),
-                     ("eval", eval_fixtures), ("multiscale", multiscale_fixture), ("regional", regional_fixtures)):
+                     ("eval", eval_fixtures), ("multiscale", multiscale_fixture), ("regional", regional_fixtures),
+                     ("losses", losses_fixtures), ("net", net_fixtures)):
         if not only or name in only:
             fn()
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

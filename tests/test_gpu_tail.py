@@ -312,19 +312,46 @@ def test_cpu_tensor_is_rejected():
         head(torch.zeros(1, 16, 2, 2))
 
 
-def test_full_size_properties():
-    """BASELINE.json config 2 at full size: unit norms, batch-order equivariance, determinism."""
+@pytest.mark.parametrize("p", [3.0, 2.7])
+def test_full_size_all_images(p):
+    """BASELINE.json config 2 at full size (64 x 2048 x 32 x 32, whitening 2048 -> 2048), p = 3 and a non-integer exponent:
+    ALL 64 descriptors against the oracle; unit norms, batch-order equivariance, determinism."""
     torch.manual_seed(4)
     x = torch.relu(torch.randn(64, 2048, 32, 32, device=DEV))
-    head = _head(2048).to(DEV)
+    head = _head(2048, p=p).to(DEV)
     with torch.no_grad():
+        head.whiten.bias.normal_(0, 0.02)
         a = head(x)
         b = head(x)
         perm = torch.randperm(64, device=DEV)
         c = head(x[perm].contiguous())
+        a_nw = head(x, do_whitening=False)
     assert torch.equal(a, b)
     np.testing.assert_allclose(a.norm(dim=0).cpu().numpy(), 1.0, atol=1e-4)
     assert float((a[:, perm] - c).abs().max()) < 1e-6
-    # a few images against the oracle at full channel count / map size
-    ref = O.head_forward(x[:4].cpu(), 3.0, 1e-6, head.whiten.weight.detach().cpu(), head.whiten.bias.detach().cpu())
-    assert _rel(a[:, :4].cpu(), ref) < RTOL
+    xc = x.cpu()
+    ref = O.head_forward(xc, p, 1e-6, head.whiten.weight.detach().cpu(), head.whiten.bias.detach().cpu())
+    assert _rel(a.cpu(), ref) < RTOL
+    np.testing.assert_allclose(a.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=1e-6)
+    assert _rel(a_nw.cpu(), O.head_forward(xc, p, 1e-6, do_whitening=False)) < RTOL
+
+
+@pytest.mark.parametrize("p", [2.2, 2.7, 3.3, 4.5, 1.5, 5.5])
+def test_general_exponent_accuracy(p):
+    """Non-integer p: half of the ex2 of x^p = ex2(p lg2 x) run as a degree-4 polynomial on the FMA pipe (tail.cu
+    poly_ex2).  Pooled values within 1e-5 relative, descriptors within 1e-4, over a wide dynamic range of activations
+    (exact zeros, values at the eps clamp, 1e-4 .. 60)."""
+    from cirtorch_b200.modules.pools import GeM
+    torch.manual_seed(int(p * 100))
+    x = torch.relu(torch.randn(6, 256, 16, 16)) * torch.logspace(-4, 1.3, 256).reshape(1, 256, 1, 1)
+    x[0, :8] = 0.0
+    x[1, :8] = 1e-6
+    x[2, 3] = 60.0
+    ref_g = O.gem(x, p)
+    got_g = GeM(p=p).to(DEV)(x.to(DEV))
+    np.testing.assert_allclose(got_g.cpu().numpy(), ref_g.numpy(), rtol=1e-5, atol=1e-30)
+    head = _head(256, p=p)
+    ref = O.head_forward(x, p, 1e-6, head.whiten.weight.detach(), head.whiten.bias.detach())
+    with torch.no_grad():
+        out = head.to(DEV)(x.to(DEV))
+    assert _rel(out.cpu(), ref) < RTOL

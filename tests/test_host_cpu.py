@@ -105,7 +105,8 @@ def test_store_formats_roundtrip(tmp_path):
         pickle.dump(train, f)
     tdb = store.load_training_db(str(tmp_path / "sfm.pkl"), "train")
     miner = store.miner_from_training_db(tdb, nnum=1, qsize=2, poolsize=6)
-    assert miner.qsize == 2 and miner.poolsize == 6 and list(miner.clusters) == [0, 0, 1, 1, 2, 2]
+    assert miner.query_size == 2 and miner.pool_size == 6 and list(miner.clusters) == [0, 0, 1, 1, 2, 2]
+    assert miner.neg_num == 1 and miner.negative_indices is None and miner.nidxs is None
     head = globalHead(pooling={"name": "GeM", "params": {"p": 3, "eps": 1e-6}}, normal={"name": "L2N", "params": {}}, dim=8)
     sd = {k: v.clone() + 1.0 for k, v in head.state_dict().items()}
     sd["whiten.bias"] = torch.zeros(3)                     # wrong shape: skipped like _load_pretraining_dict
@@ -178,7 +179,7 @@ def test_entry_points_validate_before_touching_the_device():
     assert lib.cir_tail_workspace_bytes(0, 2048, 2048, C.byref(need)) == -1
     assert lib.cir_tail_workspace_bytes(64, 2048, 2048, C.byref(need)) == 0 and need.value > 64 * 2048 * 4
     calls = {
-        "cir_tail_fwd": lambda: lib.cir_tail_fwd(None, 1, 8, 4, 4, None, 0, 1e-6, 1e-6, 0, None, None, 8, None, 8, None, 0, 0, None),
+        "cir_tail_fwd": lambda: lib.cir_tail_fwd(None, 1, 8, 4, 4, None, 0, 1e-6, 1e-6, 0, None, None, 8, None, 8, None, None, 0, 0, None),
         "cir_gem_bwd": lambda: lib.cir_gem_bwd(None, 1, 8, 4, 4, None, 0, 1e-6, None, None, None, None, None),
         "cir_region_pool": lambda: lib.cir_region_pool(None, 1, 8, 4, 4, None, 1, None, 0, 1e-6, 0, None, None),
         "cir_l2n_rows": lambda: lib.cir_l2n_rows(None, 1, 8, 8, 1e-6, None, 8, None),

@@ -120,3 +120,98 @@ def test_alpha_qe_two_restatements_agree():
     np.testing.assert_allclose(O.alpha_qe(Q, V, k=0), Q / (1 + 1e-6), rtol=1e-9)
     d = O.dba(V, k=5, alpha=3.0)
     np.testing.assert_allclose(np.linalg.norm(d, axis=0), 1.0, atol=1e-5)
+
+
+def test_losses_match_reference(golden):
+    """contrastive_loss / triplet_loss restatements (values and autograd gradients) vs losses.py:7-46."""
+    g = golden("losses")
+    for name in "abc":
+        label, msk = torch.from_numpy(g[f"{name}_label"]), torch.from_numpy(g[f"{name}_msk"])
+        for margin in (0.7, 0.1):
+            for kind, fn in (("contrastive", lambda x: O.contrastive_loss(x, label, margin, 1e-6)),
+                             ("triplet", lambda x: O.triplet_loss(x, label, msk, margin))):
+                x = torch.from_numpy(g[f"{name}_x"]).requires_grad_(True)
+                y = fn(x)
+                np.testing.assert_allclose(y.detach().numpy(), g[f"{name}_{kind}_{margin}"], rtol=1e-5, atol=1e-6)
+                if y.requires_grad:
+                    (gx,) = torch.autograd.grad(y, x)
+                    np.testing.assert_allclose(gx.numpy(), g[f"{name}_{kind}_{margin}_grad"], rtol=1e-4, atol=1e-6)
+
+
+def _net_fixture_body(g):
+    conv = torch.nn.Conv2d(3, 32, 3, stride=2, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(g["conv_w"]))
+        conv.bias.copy_(torch.from_numpy(g["conv_b"]))
+    return conv, (lambda img: {"mod5": torch.relu(conv(img))})
+
+
+def test_net_forward_matches_reference(golden):
+    """Padded ragged batch through body + head (GF_net.py / GF_algo.py): single- and multi-scale descriptors."""
+    g = golden("net")
+    _, body = _net_fixture_body(g)
+    imgs = [torch.from_numpy(g[f"img{i}"]) for i in range(4)]
+    W, b = torch.from_numpy(g["W"]), torch.from_numpy(g["b"])
+    with torch.no_grad():
+        np.testing.assert_allclose(O.net_forward(body, imgs, float(g["p"]), 1e-6, W, b).numpy(), g["pred"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(O.net_forward(body, imgs, float(g["p"]), 1e-6, W, b, scales=(1, 2 ** -0.5, 0.5)).numpy(),
+                                   g["pred_ms"], rtol=1e-5, atol=1e-7)
+        timgs = [torch.from_numpy(g[f"timg{i}"]) for i in range(8)]
+        pred = O.net_forward(body, timgs, float(g["p"]), 1e-6, W, b)
+        np.testing.assert_allclose(pred.numpy(), g["train_pred"], rtol=1e-5, atol=1e-7)
+        label = torch.tensor([-1., 1., 0., 0.] * 2)
+        loss = O.triplet_loss(pred, label, torch.arange(2).repeat_interleave(4), 0.5)
+        np.testing.assert_allclose(loss.numpy(), g["train_loss"], rtol=1e-5)
+
+
+def test_reference_net_takes_the_drop_in_algo():
+    """The reference's OWN ImageRetrievalNet (cirtorch/models/GF_net.py) built around this package's globalFeatureAlgo /
+    globalFeatureLoss: same call contract, same result as with the reference's algo.  Needs /root/reference (build
+    container only); the head here is a CPU stand-in so that no kernel is involved."""
+    import os
+    import sys
+    import types
+    import pytest
+    if not os.path.isdir("/root/reference/cirtorch"):
+        pytest.skip("the reference tree is not present on this machine")
+    sys.path.insert(0, "/root/reference")
+    if "inplace_abn" not in sys.modules:
+        stub = types.ModuleType("inplace_abn")
+        stub.ABN = stub.InPlaceABN = stub.InPlaceABNSync = type("ABN", (torch.nn.Module,), {})
+        stub.active_group = stub.set_active_group = lambda *a, **k: None
+        sys.modules["inplace_abn"] = stub
+    from cirtorch.models.GF_net import ImageRetrievalNet as RefNet
+    from cirtorch.algos.GF_algo import globalFeatureAlgo as RefAlgo, globalFeatureLoss as RefLoss
+    from cirtorch.utils.parallel import PackedSequence as RefSeq
+    from cirtorch_b200.algos.GF_algo import globalFeatureAlgo, globalFeatureLoss
+
+    class Head(torch.nn.Module):
+        def forward(self, x):
+            return O.head_forward(x, 3.0, 1e-6, do_whitening=False)
+
+    class Body(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 16, 3, padding=1)
+
+        def forward(self, img):
+            return {"mod5": torch.relu(self.conv(img))}
+
+    torch.manual_seed(0)
+    body, head = Body(), Head()
+    imgs = [torch.randn(3, 20, 16), torch.randn(3, 18, 24)]
+    mine = RefNet(body, globalFeatureAlgo(globalFeatureLoss("triplet", 0.5), min_level=2, fpn_levels=1), head, augment=None).eval()
+    ref = RefNet(body, RefAlgo(RefLoss("triplet", 0.5), min_level=2, fpn_levels=1), head, augment=None).eval()
+    with torch.no_grad():
+        for scales in ([1], [1, 0.5]):
+            a = mine(img=RefSeq(imgs), scales=scales, do_prediction=True)[1]["ret_pred"]
+            b = ref(img=RefSeq(imgs), scales=scales, do_prediction=True)[1]["ret_pred"]
+            assert torch.equal(a, b)
+    # FPN-style list input and the error for anything else (GF_algo.py:51-59)
+    algo = globalFeatureAlgo(None, min_level=1, fpn_levels=2)
+    assert algo._get_level(["l0", "l1", "l2", "l3"]) == "l1"
+    try:
+        algo._get_level(torch.zeros(1))
+        raise AssertionError("expected NameError")
+    except NameError:
+        pass
