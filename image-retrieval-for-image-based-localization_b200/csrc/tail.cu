@@ -43,9 +43,11 @@ constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 consume, warp 15 produces
 constexpr int TAIL_NT = 128;                         // output dims per projection unit (UMMA N)
 constexpr int TAIL_KS = 256;                         // K slice per projection unit (4 k blocks of 64)
-constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows, <= 16 KB
-constexpr int TAIL_MAX_SLOTS = 8;
-constexpr int TAIL_MAX_BARS = 32;
+constexpr int TAIL_SLOT_BYTES = 16384;               // phase B ring slot (one 128 x 64 bf16 A tile); phase A slots are <= this
+constexpr int TAIL_ASLOT_MIN = 4096;                 // phase A ring slot: whole rows, 4 KB .. 16 KB (TailParams::aslot_bytes)
+constexpr int TAIL_MAX_SLOTS = 8;                    // 16 KB slots in the ring
+constexpr int TAIL_MAX_ASLOTS = TAIL_MAX_SLOTS * (TAIL_SLOT_BYTES / TAIL_ASLOT_MIN);
+constexpr int TAIL_MAX_BARS = 64;
 constexpr int TAIL_MB = 128;                         // images per phase-B pass (UMMA M)
 constexpr int TAIL_BT_BYTES = TAIL_NT * 128;         // one B tile: 128 rows x 64 k bf16, 128 B swizzle (16 KB)
 constexpr int TAIL_W_BYTES = (TAIL_KS / 64) * 2 * TAIL_BT_BYTES;   // hi + lo tiles of a unit's W tile: 128 KB
@@ -74,7 +76,9 @@ struct TailParams {
     unsigned flags;
     int bulk_ok;       // rows can be moved by cp.async.bulk
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
-    int n_slots;       // ring slots
+    int n_slots;       // 16 KB ring slots (phase B)
+    int n_aslots;      // phase A ring slots of aslot_bytes each (same shared memory)
+    int aslot_bytes;
     int w_bytes;       // shared-memory bytes reserved for the W slice
     int gen_mode;      // exponent class of a non-integer p on vector rows: PM_GENERAL or PM_GENERAL_POLY0 + NPOLY
     unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
@@ -157,22 +161,33 @@ __device__ __forceinline__ int classify_p(int pool_mode, float p, int gen_mode =
     return gen_mode;
 }
 
+// 128-bit load from shared memory by its 32-bit shared address.  The ring pointer is derived from an aligned-up uintptr_t,
+// so plain C++ loads through it compile to GENERIC loads (LD.E.128: address-space check, long-scoreboard latency) --
+// ncu showed the consumers' first arithmetic instruction of every row waiting on them.  volatile: ordered after the
+// mbarrier wait that makes the row visible and before the arrive that hands the slot back.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+    return r;
+}
+
 // per-lane partial of one row held as float4s (shared or global memory), lanes stride the vectors
 template <int PM, bool GLOBAL>
 __device__ __forceinline__ float row_partial_vec(const float4* v, int nvec, int lane, float eps, float p) {
     float a0 = PM == PM_MAX ? -INFINITY : 0.0f, a1 = a0;
+    const uint32_t sa = GLOBAL ? 0u : smem_u32(v);
     int i = lane;
     for (; i + 32 * 7 < nvec; i += 256) {
         float4 u[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = GLOBAL ? ld_stream_f4(v + i + 32 * j) : v[i + 32 * j];
+        for (int j = 0; j < 8; ++j) u[j] = GLOBAL ? ld_stream_f4(v + i + 32 * j) : lds_f4(sa + (uint32_t)(i + 32 * j) * 16u);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
             a0 = fold4<PM>(a0, u[j], eps, p);
             a1 = fold4<PM>(a1, u[j + 1], eps, p);
         }
     }
-    for (; i < nvec; i += 32) a0 = fold4<PM>(a0, GLOBAL ? ld_stream_f4(v + i) : v[i], eps, p);
+    for (; i < nvec; i += 32) a0 = fold4<PM>(a0, GLOBAL ? ld_stream_f4(v + i) : lds_f4(sa + (uint32_t)i * 16u), eps, p);
     return PM == PM_MAX ? fmaxf(a0, a1) : a0 + a1;
 }
 template <int PM>
@@ -343,14 +358,14 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
         const int HW = P.HW;
         const bool gem = P.pool_mode == CIR_POOL_GEM;
 
-        // lane l of a consumer warp parks the statistic of the l-th row of the current batch of 32
+        // lane l of a consumer warp parks the statistic of the l-th row of the current batch of 32, with its (image, channel)
         float held = 0.0f;
-        long long held_row = -1;
+        int held_n = -1, held_c = 0;
         int nheld = 0;
         auto flush = [&]() {
-            if (held_row >= 0) {
-                const int c = (int)(held_row % P.C);
-                const long long n = held_row / P.C;
+            if (held_n >= 0) {
+                const int c = held_c;
+                const long long n = held_n;
                 const float pl = gem ? __ldg(P.p + c * P.p_stride) : 1.0f;
                 const float v = finish_row(classify_p(P.pool_mode, pl), held, HW, pl);
                 if (P.pooled_out) P.pooled_out[n * P.C + c] = v;
@@ -363,18 +378,45 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     P.pooled[n * P.pooled_ld + c] = v;
                 }
             }
-            held_row = -1;
+            held_n = -1;
         };
-        auto take = [&](float a, long long row) {
-            if (lane == (nheld & 31)) { held = a; held_row = row; }
+        auto take = [&](float a, int n, int c) {
+            if (lane == (nheld & 31)) { held = a; held_n = n; held_c = c; }
             if ((++nheld & 31) == 0) flush();
         };
+        // The (image, channel) of a warp's current row is tracked incrementally: a 64-bit division / modulo per row (and two
+        // per flushed row) cost more issue slots than the arithmetic of the row itself (ncu, r2c: ~170 of ~360 warp
+        // instructions per row were index arithmetic, which held the MUFU pipe of the general exponent at 51 %).
+        const int row_step = P.bulk_ok ? TAIL_CONSUMERS : TAIL_WARPS;     // rows between two rows of one warp
+        int cur_n = 0, cur_c = 0;
+        {
+            const long long first = r0 + warp;
+            cur_n = (int)(first / P.C);
+            cur_c = (int)(first - (long long)cur_n * P.C);
+        }
+        const bool wide = P.C >= row_step;            // the usual case: at most one image boundary per step
+        auto next_row = [&]() {
+            cur_c += row_step;
+            if (wide) {
+                const bool wrap = cur_c >= P.C;
+                cur_c -= wrap ? P.C : 0;
+                cur_n += wrap ? 1 : 0;
+            } else {
+                while (cur_c >= P.C) { cur_c -= P.C; ++cur_n; }
+            }
+        };
+        // one exponent for all channels: load and classify it once
+        const float p_shared = (gem && P.p_stride == 0) ? __ldg(P.p) : 1.0f;
 
         if (P.bulk_ok) {
-            const int rps = max(1, TAIL_SLOT_BYTES / (HW * 4));            // rows per slot
+            // Phase A slot size: 16 KB.  Smaller slots pin less of the ring while rows are being reduced, but the stream then
+            // moves in smaller bulk copies and collapses (measured at 64 x 2048 x 32 x 32, p = 3: 16 KB slots 98.8 us,
+            // 8 KB 120.9 us, 4 KB 204.8 us per launch); CIR_TAIL_ASLOT keeps the experiment reachable.
+            const int n_slots = P.n_aslots;
+            const int rps = max(1, P.aslot_bytes / (HW * 4));              // rows per slot
             const int iters = (my_rows + rps - 1) / rps;
             // gap between two rows of a consumer warp: at most TAIL_CONSUMERS iterations (+1)
-            const int nbar = min(TAIL_MAX_BARS, P.n_slots * ((TAIL_CONSUMERS + 1 + P.n_slots - 1) / P.n_slots + 1));
+            const int nbar = min(TAIL_MAX_BARS, n_slots * ((TAIL_CONSUMERS + 1 + n_slots - 1) / n_slots + 1));
             if (tid == 0) {
                 for (int s = 0; s < nbar; ++s) {
                     mbar_init(&full_bar[s], 1);
@@ -389,16 +431,16 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     int slot = 0, bar = 0, ebar = 0;          // data slot, barrier of iteration t, barrier of iteration t - n_slots
                     uint32_t epar = 0;
                     for (int t = 0; t < iters; ++t) {
-                        if (t >= P.n_slots) {                  // the slot's previous rows (iteration t - n_slots) are consumed
+                        if (t >= n_slots) {                  // the slot's previous rows (iteration t - n_slots) are consumed
                             mbar_wait(&empty_bar[ebar], epar);
                             if (++ebar == nbar) { ebar = 0; epar ^= 1u; }
                         }
                         const int nr = min(rps, my_rows - t * rps);
                         const uint32_t bytes = (uint32_t)nr * (uint32_t)HW * 4u;
                         mbar_arrive_expect_tx(&full_bar[bar], bytes);
-                        bulk_load(ring + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
+                        bulk_load(ring + (size_t)slot * P.aslot_bytes, P.x + (r0 + (long long)t * rps) * HW, bytes,
                                   &full_bar[bar], pol);
-                        if (++slot == P.n_slots) slot = 0;
+                        if (++slot == n_slots) slot = 0;
                         if (++bar == nbar) bar = 0;
                     }
                 }
@@ -413,22 +455,35 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     const int conv_every = max(1, my_count / (CONV_BATCHES + 1));
                     int conv_done = 0, taken = 0;
                     // warp w takes local rows w, w + NC, ...; it only touches the barriers of the slots holding them
-                    int j = warp, slot = 0, bar = 0;
-                    uint32_t par = 0;
-                    for (int i = warp; i < my_rows; i += NC, j += NC) {
-                        while (j >= rps) {                      // advance to the slot iteration holding row i
-                            j -= rps;
-                            if (++slot == P.n_slots) slot = 0;
-                            if (++bar == nbar) { bar = 0; par ^= 1u; }
-                        }
+                    // slot iterations / rows inside the slot between two rows of this warp (NC = q * rps + r); the two possible
+                    // advances (q or q + 1 iterations) are reduced modulo the ring sizes once, so that the per-row update is a
+                    // few selects instead of loops
+                    const int step_q = NC / rps, step_r = NC - step_q * rps;
+                    const int sl0 = step_q % n_slots, sl1 = (step_q + 1) % n_slots;
+                    const int ba0 = step_q % nbar, ba1 = (step_q + 1) % nbar;
+                    const uint32_t fl0 = (uint32_t)(step_q / nbar) & 1u, fl1 = (uint32_t)((step_q + 1) / nbar) & 1u;
+                    int j = warp % rps;
+                    int slot = (warp / rps) % n_slots, bar = (warp / rps) % nbar;
+                    uint32_t par = (uint32_t)((warp / rps) / nbar) & 1u;
+                    const int pm_shared = classify_p(P.pool_mode, p_shared, P.gen_mode);
+                    for (int i = warp; i < my_rows; i += NC) {
                         mbar_wait(&full_bar[bar], par);
-                        const long long row = r0 + i;
-                        const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
-                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
-                        const float a = row_reduce<false>(classify_p(P.pool_mode, pr, P.gen_mode), src, HW, true, lane, P.eps_gem, pr);
+                        const float pr = (gem && P.p_stride) ? __ldg(P.p + cur_c) : p_shared;
+                        const int pm = (gem && P.p_stride) ? classify_p(P.pool_mode, pr, P.gen_mode) : pm_shared;
+                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * P.aslot_bytes) + (size_t)j * HW;
+                        const float a = row_reduce<false>(pm, src, HW, true, lane, P.eps_gem, pr);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
-                        take(a, row);
+                        take(a, cur_n, cur_c);
+                        next_row();
+                        j += step_r;                            // advance to the slot iteration holding row i + NC
+                        const bool carry = j >= rps;
+                        j -= carry ? rps : 0;
+                        slot += carry ? sl1 : sl0;
+                        slot -= slot >= n_slots ? n_slots : 0;
+                        bar += carry ? ba1 : ba0;
+                        par ^= carry ? fl1 : fl0;
+                        if (bar >= nbar) { bar -= nbar; par ^= 1u; }
                         if (own_unit && conv_done < CONV_BATCHES && ++taken == (conv_done + 1) * conv_every) {
                             convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, 1);
                             ++conv_done;
@@ -445,10 +500,11 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
             // direct loads: every warp takes rows r0 + warp, r0 + warp + 16, ...
             for (int j = warp; j < my_rows; j += TAIL_WARPS) {
                 const long long row = r0 + j;
-                const float pr = gem ? __ldg(P.p + (int)(row % P.C) * P.p_stride) : 1.0f;
+                const float pr = (gem && P.p_stride) ? __ldg(P.p + cur_c) : p_shared;
                 const float a = row_reduce<true>(classify_p(P.pool_mode, pr, P.vec_ok ? P.gen_mode : PM_GENERAL), P.x + row * HW, HW, P.vec_ok != 0, lane,
                                                P.eps_gem, pr);
-                take(a, row);
+                take(a, cur_n, cur_c);
+                next_row();
             }
             flush();
         }
@@ -749,6 +805,12 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.pooled_out = pool_only ? nullptr : pooled_out;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
+    P.aslot_bytes = TAIL_SLOT_BYTES;
+    {
+        static const char* dbg = getenv("CIR_TAIL_ASLOT");        // experiments: 4096 / 8192 / 16384
+        if (dbg && (atoi(dbg) == 4096 || atoi(dbg) == 8192 || atoi(dbg) == 16384) && (size_t)P.HW * 4 <= (size_t)atoi(dbg))
+            P.aslot_bytes = atoi(dbg);
+    }
     {
         // non-integer exponent: how many of every 4 ex2 go to the FMA pipe (CIR_TAIL_NPOLY = 0..4 for experiments)
         static const char* dbg = getenv("CIR_TAIL_NPOLY");
@@ -789,6 +851,7 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     if (slots > TAIL_MAX_SLOTS) slots = TAIL_MAX_SLOTS;
     CIR_REQUIRE(slots >= (whiten ? 2 : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
     P.n_slots = slots;
+    P.n_aslots = slots * (TAIL_SLOT_BYTES / P.aslot_bytes);
     const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES + 1024 /* 1 KB alignment of the tiles */;
     CUtensorMap tmHi, tmLo;
     memset(&tmHi, 0, sizeof(tmHi));

@@ -16,7 +16,7 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 if what == "tail":
     from bench import make_head, B, C, H, W
-    head = make_head(dev)
+    head = make_head(dev, p=float(os.environ.get("CIR_PROFILE_P", "3.0")))
     xs = [torch.relu(torch.randn((B, C, H, W), device=dev)) for _ in range(2)]
     with torch.no_grad():
         for i in range(n):
