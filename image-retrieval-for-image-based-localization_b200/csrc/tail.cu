@@ -43,15 +43,13 @@ constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 consume, warp 15 produces
 constexpr int TAIL_NT = 128;                         // output dims per projection unit (UMMA N)
 constexpr int TAIL_KS = 256;                         // K slice per projection unit (4 k blocks of 64)
-constexpr int TAIL_SLOT_BYTES = 16384;               // phase B ring slot (one 128 x 64 bf16 A tile); phase A slots are <= this
-constexpr int TAIL_ASLOT_MIN = 4096;                 // phase A ring slot: whole rows, 4 KB .. 16 KB (TailParams::aslot_bytes)
-constexpr int TAIL_MAX_SLOTS = 8;                    // 16 KB slots in the ring
-constexpr int TAIL_MAX_ASLOTS = TAIL_MAX_SLOTS * (TAIL_SLOT_BYTES / TAIL_ASLOT_MIN);
-constexpr int TAIL_MAX_BARS = 64;
+constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows (phase A) / one 128 x 64 bf16 A tile (phase B)
+constexpr int TAIL_MAX_SLOTS = 8;
+constexpr int TAIL_MAX_BARS = 32;
 constexpr int TAIL_MB = 128;                         // images per phase-B pass (UMMA M)
 constexpr int TAIL_BT_BYTES = TAIL_NT * 128;         // one B tile: 128 rows x 64 k bf16, 128 B swizzle (16 KB)
 constexpr int TAIL_W_BYTES = (TAIL_KS / 64) * 2 * TAIL_BT_BYTES;   // hi + lo tiles of a unit's W tile: 128 KB
-constexpr int TAIL_NPOLY_DEFAULT = 2;                 // general exponent: 2 of every 4 ex2 on the FMA pipe
+constexpr int TAIL_NPOLY_DEFAULT = 1;                 // general exponent: 1 of every 4 ex2 on the FMA pipe
 constexpr size_t TAIL_STAMP_BYTES = 1024 * 8 * 8;    // debug time stamps: up to 1024 CTAs x 8 slots
 
 struct TailParams {
@@ -76,9 +74,7 @@ struct TailParams {
     unsigned flags;
     int bulk_ok;       // rows can be moved by cp.async.bulk
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
-    int n_slots;       // 16 KB ring slots (phase B)
-    int n_aslots;      // phase A ring slots of aslot_bytes each (same shared memory)
-    int aslot_bytes;
+    int n_slots;       // ring slots
     int w_bytes;       // shared-memory bytes reserved for the W slice
     int gen_mode;      // exponent class of a non-integer p on vector rows: PM_GENERAL or PM_GENERAL_POLY0 + NPOLY
     unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
@@ -131,9 +127,13 @@ __device__ __forceinline__ float poly_ex2(float t) {
 __device__ __forceinline__ float fold_poly(float acc, float v, float eps, float p) {
     return acc + poly_ex2(p * fast_lg2(fmaxf(v, eps)));
 }
-// General exponent: x^p = ex2(p * lg2 x) costs two MUFU operations per element, and the MUFU pipe (4 lanes per clock and SM
-// sub-partition), not HBM, then bounds the stream (117 us vs 99 us for p = 3 at 64 x 2048 x 32 x 32).  PM_GENERAL + NPOLY sends
-// NPOLY of every 4 ex2 to the FMA pipe instead (poly_ex2), which balances the two pipes.
+// General exponent: x^p = ex2(p * lg2 x) costs two MUFU operations per element (4 lanes per clock and SM sub-partition:
+// 8.7 cycles per warp instruction measured, scripts/pow_microbench.cu).  PM_GENERAL_POLY0 + NPOLY sends NPOLY of every 4 ex2
+// to the FMA pipe instead (poly_ex2).  Compute only (rows resident in shared memory, no HBM stream) the 32-element step
+// costs 17.3 cycles per sub-partition with NPOLY = 0, 15.3 / 13.9 / 15.2 / 17.7 with 1 / 2 / 3 / 4 -- all inside the 22.2
+// cycles the HBM stream leaves.  Inside the kernel (per launch, 64 x 2048 x 32 x 32, p = 2.7): 110.7 / 109.3 / 113.3 /
+// 120.3 us for NPOLY 0 / 1 / 2 / 3: the extra FMA-pipe instructions compete with the per-row bookkeeping for issue slots,
+// so only NPOLY = 1 pays.
 template <int PM>
 __device__ __forceinline__ float fold4(float acc, const float4& v, float eps, float p) {
     if (PM >= PM_GENERAL_POLY0) {
@@ -214,9 +214,6 @@ __device__ __forceinline__ float row_reduce(int pm, const float* row, int HW, bo
         CIR_ROW_CASE(PM_MAX)
         CIR_ROW_CASE(PM_MEAN)
         case PM_GENERAL_POLY0 + 1: a = row_partial_vec<PM_GENERAL_POLY0 + 1, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
-        case PM_GENERAL_POLY0 + 2: a = row_partial_vec<PM_GENERAL_POLY0 + 2, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
-        case PM_GENERAL_POLY0 + 3: a = row_partial_vec<PM_GENERAL_POLY0 + 3, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
-        case PM_GENERAL_POLY0 + 4: a = row_partial_vec<PM_GENERAL_POLY0 + 4, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
         default:
             a = vec ? row_partial_vec<PM_GENERAL, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p)
                     : row_partial_scalar<PM_GENERAL>(row, HW, lane, eps, p);
@@ -409,11 +406,11 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
         const float p_shared = (gem && P.p_stride == 0) ? __ldg(P.p) : 1.0f;
 
         if (P.bulk_ok) {
-            // Phase A slot size: 16 KB.  Smaller slots pin less of the ring while rows are being reduced, but the stream then
-            // moves in smaller bulk copies and collapses (measured at 64 x 2048 x 32 x 32, p = 3: 16 KB slots 98.8 us,
-            // 8 KB 120.9 us, 4 KB 204.8 us per launch); CIR_TAIL_ASLOT keeps the experiment reachable.
-            const int n_slots = P.n_aslots;
-            const int rps = max(1, P.aslot_bytes / (HW * 4));              // rows per slot
+            // Slot size: 16 KB.  Smaller slots pin less of the ring while rows are being reduced, but the stream then moves
+            // in smaller bulk copies and collapses (measured at 64 x 2048 x 32 x 32, p = 3: 16 KB slots 98.8 us, 8 KB
+            // 120.9 us, 4 KB 204.8 us per launch).
+            const int n_slots = P.n_slots;
+            const int rps = max(1, TAIL_SLOT_BYTES / (HW * 4));              // rows per slot
             const int iters = (my_rows + rps - 1) / rps;
             // gap between two rows of a consumer warp: at most TAIL_CONSUMERS iterations (+1)
             const int nbar = min(TAIL_MAX_BARS, n_slots * ((TAIL_CONSUMERS + 1 + n_slots - 1) / n_slots + 1));
@@ -438,7 +435,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         const int nr = min(rps, my_rows - t * rps);
                         const uint32_t bytes = (uint32_t)nr * (uint32_t)HW * 4u;
                         mbar_arrive_expect_tx(&full_bar[bar], bytes);
-                        bulk_load(ring + (size_t)slot * P.aslot_bytes, P.x + (r0 + (long long)t * rps) * HW, bytes,
+                        bulk_load(ring + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
                                   &full_bar[bar], pol);
                         if (++slot == n_slots) slot = 0;
                         if (++bar == nbar) bar = 0;
@@ -470,7 +467,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         mbar_wait(&full_bar[bar], par);
                         const float pr = (gem && P.p_stride) ? __ldg(P.p + cur_c) : p_shared;
                         const int pm = (gem && P.p_stride) ? classify_p(P.pool_mode, pr, P.gen_mode) : pm_shared;
-                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * P.aslot_bytes) + (size_t)j * HW;
+                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
                         const float a = row_reduce<false>(pm, src, HW, true, lane, P.eps_gem, pr);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
@@ -805,16 +802,11 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.pooled_out = pool_only ? nullptr : pooled_out;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
-    P.aslot_bytes = TAIL_SLOT_BYTES;
     {
-        static const char* dbg = getenv("CIR_TAIL_ASLOT");        // experiments: 4096 / 8192 / 16384
-        if (dbg && (atoi(dbg) == 4096 || atoi(dbg) == 8192 || atoi(dbg) == 16384) && (size_t)P.HW * 4 <= (size_t)atoi(dbg))
-            P.aslot_bytes = atoi(dbg);
-    }
-    {
-        // non-integer exponent: how many of every 4 ex2 go to the FMA pipe (CIR_TAIL_NPOLY = 0..4 for experiments)
+        // non-integer exponent: how many of every 4 ex2 go to the FMA pipe (CIR_TAIL_NPOLY = 0 / 1 for experiments; 2..4
+        // were measured and lost, see the comment at fold4)
         static const char* dbg = getenv("CIR_TAIL_NPOLY");
-        const int npoly = (dbg && dbg[0] >= '0' && dbg[0] <= '4') ? dbg[0] - '0' : TAIL_NPOLY_DEFAULT;
+        const int npoly = (dbg && dbg[0] >= '0' && dbg[0] <= '1') ? dbg[0] - '0' : TAIL_NPOLY_DEFAULT;
         P.gen_mode = npoly == 0 ? PM_GENERAL : PM_GENERAL_POLY0 + npoly;
     }
 
@@ -851,7 +843,6 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     if (slots > TAIL_MAX_SLOTS) slots = TAIL_MAX_SLOTS;
     CIR_REQUIRE(slots >= (whiten ? 2 : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
     P.n_slots = slots;
-    P.n_aslots = slots * (TAIL_SLOT_BYTES / P.aslot_bytes);
     const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES + 1024 /* 1 KB alignment of the tiles */;
     CUtensorMap tmHi, tmLo;
     memset(&tmHi, 0, sizeof(tmHi));

@@ -31,10 +31,10 @@ for p in (2.7, 3.0):
         torch.cuda.synchronize()
         per = sorted(1e3 * ev[i].elapsed_time(ev[i + 1]) for i in range(40))
         print("   per-launch us: min %%.1f median %%.1f max %%.1f" %% (per[0], per[20], per[-1]))
-    print("aslot=%%s npoly=%%s p=%%.1f us_per_launch=%%.2f  sm_mhz(min/median)=%%d/%%d  power_w(max)=%%.0f" %% (os.environ.get("CIR_TAIL_ASLOT"), os.environ.get("CIR_TAIL_NPOLY", "default"), p,
+    print("dynamic=%%s npoly=%%s p=%%.1f us_per_launch=%%.2f  sm_mhz(min/median)=%%d/%%d  power_w(max)=%%.0f" %% (os.environ.get("CIR_TAIL_DYNAMIC"), os.environ.get("CIR_TAIL_NPOLY", "default"), p,
           1e3 * e0.elapsed_time(e1) / 400, min(mhz), sorted(mhz)[len(mhz) // 2], max(watts)))
 """ % (ROOT, ROOT)
-for n, a in (("0", "16384"), ("1", "16384"), ("2", "16384"), ("3", "16384"), ("0", "16384"), ("1", "16384"), ("2", "16384")):
-    env = dict(os.environ, CIR_TAIL_NPOLY=n, CIR_TAIL_ASLOT=a)
+for n, a in (("0", "0"), ("0", "1"), ("1", "0"), ("1", "1"), ("2", "1"), ("0", "1"), ("1", "1")):
+    env = dict(os.environ, CIR_TAIL_NPOLY=n, CIR_TAIL_DYNAMIC=a)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
     print(r.stdout.strip() or r.stderr[-500:])
