@@ -37,15 +37,16 @@ def _like(result: torch.Tensor, template):
 
 def _result_dtype(*arrays):
     """numpy's promotion of the reference expression (fp32 X with the fp64 m, P of whitenlearn gives fp64)."""
-    return np.result_type(*[(a.detach().cpu().numpy()[:0] if torch.is_tensor(a) else np.asarray(a)[:0]) for a in arrays])
+    return np.result_type(*[np.asarray(a).dtype for a in arrays])
 
 
 def whitenapply(X, m, P, dimensions=None):
     """whiten.py:4-12:  Y = P[:dimensions] (X - m);  Y /= (||Y||_2 over axis 0 + 1e-6).   X: D x N.
 
     One pass: Y = X W^T + b with W = P[:dimensions] and b = -W m folded into the bias of the L2N kernel (no centred
-    copy of X is materialised).  The projection runs on the tcgen05 GEMM with bf16x3 operands (~1e-6 relative); the
-    result carries numpy's result dtype of the reference expression (fp64 for the fp64 m, P of whitenlearn)."""
+    copy of X is materialised).  The projection runs on the tcgen05 GEMM with bf16x3 operands (~1e-6 relative).
+    numpy in -> numpy out with numpy's result dtype of the reference expression (fp64 for the fp64 m, P of whitenlearn);
+    a torch tensor X stays on the device and the result is the fp32 D' x N view of the kernel's output."""
     lib = _lib.load()
     if not dimensions:
         dimensions = P.shape[0]
@@ -62,9 +63,9 @@ def whitenapply(X, m, P, dimensions=None):
         rc = lib.cir_bias_l2n_rows(_lib.ptr(out), N, dimensions, dimensions, _lib.ptr(bias), 1e-6, _lib.ptr(out), dimensions,
                                    _lib.stream_of(out))
         _lib.check(rc, "cir_bias_l2n_rows")
-    res = out.t()
-    want = torch.from_numpy(np.zeros(0, dtype=_result_dtype(X, m, P))).dtype
-    return _like(res if res.dtype == want else res.to(want), X)
+    if torch.is_tensor(X):
+        return out.t()
+    return out.t().cpu().numpy().astype(_result_dtype(X, m, P), copy=False)
 
 
 def cholesky(S):

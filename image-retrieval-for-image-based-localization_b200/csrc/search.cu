@@ -394,203 +394,6 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------
-// CTA-pair variant of the top-k search (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster (one TPC) share every
-// database tile.  CTA r of the pair owns query tile 2 * m2 + r (its 128 TMEM lanes) and loads HALF of the 256 database
-// rows of a stage; one thread of the leader issues 256 x 256 x 16 UMMAs that read A from both CTAs' shared memory and
-// the two B halves, so per CTA a k-block costs 16 + 16 KB of L2->SM traffic instead of 16 + 32 KB, and the freed shared
-// memory holds 6 stages instead of 4.  Barriers: the leader's `full` collects the bytes of both CTAs' TMA loads; `empty`
-// and `tfull` are armed in both CTAs by a multicast tcgen05.commit; the epilogue warps of both CTAs arrive on the
-// leader's `tempty`.
-// ---------------------------------------------------------------------------------------
-constexpr int STAGES2 = 6;
-constexpr int B2_BYTES = (BN / 2) * BK * 2;                // 16 KB: this CTA's half of the database tile
-constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;           // 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-__global__ void __launch_bounds__(SEARCH_THREADS, 1)
-search2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, const SearchParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
-    uint64_t* full = bars;                  // [STAGES2]  TMA (both CTAs) -> MMA, used in the leader
-    uint64_t* empty = bars + STAGES2;       // [STAGES2]  MMA -> TMA, multicast to both CTAs
-    uint64_t* tfull = bars + 2 * STAGES2;   // [2]        MMA -> epilogue, multicast to both CTAs
-    uint64_t* tempty = tfull + 2;           // [2]        epilogues of both CTAs -> MMA, used in the leader
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmBh);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES2; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 256);        // 128 epilogue threads of each CTA
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) {
-        tmem_alloc2(tmem_slot, 512);
-        tmem_relinquish2();
-    }
-    tc_fence_before();
-    cluster_sync_all();                         // both CTAs' barriers exist before anyone signals across
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================================================================ TMA producer (both CTAs)
-        if (lane == 0) {
-            const uint64_t pol_a = policy_evict_last();
-            const uint64_t pol_b = P.b_policy == 1 ? policy_evict_first() : (P.b_policy == 2 ? policy_evict_normal() : policy_evict_last());
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = pair; u < P.units; u += npairs) {
-                const int m = (u % P.mt) * 2 + (int)rank, s = u / P.mt;
-                const int n0 = s * P.tps, n1 = min(P.nt, n0 + P.tps);
-                for (int n = n0; n < n1; ++n) {
-                    for (int kb = 0; kb < P.kblocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1u);
-                        uint8_t* a = smem + stage * STAGE2_BYTES;
-                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
-                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-                        tma2_load_2d_hint(a, &tmA, lead_full, kb * BK, m * BM, pol_a);
-                        tma2_load_2d_hint(a + A_BYTES, &tmBh, lead_full, kb * BK, n * BN + (int)rank * (BN / 2), pol_b);
-                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int u = pair; u < P.units; u += npairs) {
-                const int s = u / P.mt;
-                const int n0 = s * P.tps, n1 = min(P.nt, n0 + P.tps);
-                for (int n = n0; n < n1; ++n) {
-                    mbar_wait(&tempty[acc], acc_phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < P.kblocks; ++kb) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
-                        const uint64_t da = make_sw128_desc(a_addr);
-                        const uint64_t db = make_sw128_desc(a_addr + A_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            umma2_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                                       (uint32_t)((kb | kk) != 0));
-                        umma2_commit_mc(&empty[stage], 3);     // frees the stage in both CTAs
-                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
-                    }
-                    umma2_commit_mc(&tfull[acc], 3);           // accumulators (128 lanes in each CTA) complete
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ================================================================ epilogue (both CTAs, own 128 query rows)
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t lead_tempty0 = mapa_u32(smem_u32(&tempty[0]), 0);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int u = pair; u < P.units; u += npairs) {
-            const int m = (u % P.mt) * 2 + (int)rank, s = u / P.mt;
-            const int n0 = s * P.tps, n1 = min(P.nt, n0 + P.tps);
-            const int qg = m * BM + row;
-            const bool valid = qg < P.Q;
-            unsigned long long* L = P.lists + ((size_t)s * P.Qpad + qg) * P.cap;
-            int cnt = 0;
-            float tau = -INFINITY;
-            if (valid && P.tau0) tau = nextafterf(__ldg(P.tau0 + qg), -INFINITY);
-            for (int n = n0; n < n1; ++n) {
-                mbar_wait(&tfull[acc], acc_phase);
-                tc_fence_after();
-                const int col0 = n * BN;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + (uint32_t)(acc * BN + c * 32), v);
-                    tmem_ld_wait();
-                    const int cb = col0 + c * 32;
-                    if (valid) {
-                        if (cb + 32 > P.N) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float sc = __uint_as_float(v[j]);
-                                if (sc > tau && cb + j < P.N)
-                                    L[cnt++] = ((unsigned long long)(uint32_t)(cb + j) << 32) | (unsigned long long)v[j];
-                            }
-                        } else {
-                            uint32_t off = (uint32_t)cnt * 8u;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const uint32_t ix = (uint32_t)(cb + j);
-                                asm volatile(
-                                    "{\n\t"
-                                    ".reg .pred p;\n\t"
-                                    ".reg .u64 a;\n\t"
-                                    "setp.gt.f32 p, %2, %3;\n\t"
-                                    "@p cvt.u64.u32 a, %0;\n\t"
-                                    "@p add.u64 a, a, %1;\n\t"
-                                    "@p st.global.v2.b32 [a], {%4, %5};\n\t"
-                                    "@p add.u32 %0, %0, 8;\n\t"
-                                    "}"
-                                    : "+r"(off)
-                                    : "l"(L), "f"(__uint_as_float(v[j])), "f"(tau), "r"(v[j]), "r"(ix)
-                                    : "memory");
-                            }
-                            cnt = (int)(off >> 3);
-                        }
-                    }
-                    const unsigned need = __ballot_sync(0xffffffffu, valid && (cnt + 32 > P.cap));
-                    if (need) {
-                        __syncwarp();
-                        unsigned todo = need;
-                        while (todo) {
-                            const int l = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const int n_l = __shfl_sync(0xffffffffu, cnt, l);
-                            unsigned long long* Ll = P.lists + ((size_t)s * P.Qpad + (m * BM + quad * 32 + l)) * P.cap;
-                            int nc;
-                            float nt_;
-                            compact_dispatch(Ll, n_l, P.k, P.cap, lane, &nc, &nt_);
-                            if (lane == l) { cnt = nc; tau = fmaxf(tau, nt_); }
-                        }
-                    }
-                }
-                tc_fence_before();
-                if (rank == 0) mbar_arrive(&tempty[acc]);
-                else mbar_arrive_cluster(lead_tempty0 + (uint32_t)(acc * 8));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            }
-            P.counts[(size_t)s * P.Qpad + qg] = valid ? cnt : 0;
-        }
-    }
-
-    tc_fence_before();
-    cluster_sync_all();                         // the leader's MMAs read the peer's shared memory until the very end
-    if (warp == 2) tmem_dealloc2(tmem_base, 512);
-}
-
-// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -655,83 +458,6 @@ SearchPlan plan_search(int Q, long long N, int num_sms) {
     p.S = (p.nt + best_tps - 1) / best_tps;
     p.units = p.mt * p.S;
     return p;
-}
-
-// pair plan: query tiles are taken two at a time (one per CTA of the pair), units are spread over the CTA pairs
-static SearchPlan plan_search2(int Q, long long N, int num_sms) {
-    SearchPlan p{};
-    const int mt2 = (Q + 2 * BM - 1) / (2 * BM);
-    const int npairs = num_sms / 2;
-    p.mt = mt2;
-    p.nt = (int)((N + BN - 1) / BN);
-    p.Qpad = mt2 * 2 * BM;
-    long long best_cost = -1;
-    int best_tps = 1;
-    for (int tps = 1; tps <= p.nt; ++tps) {
-        const int S = (p.nt + tps - 1) / tps;
-        const long long units = (long long)mt2 * S;
-        const long long waves = (units + npairs - 1) / npairs;
-        const long long cost = waves * (tps + 1);
-        if (best_cost < 0 || cost < best_cost || (cost == best_cost && tps > best_tps)) {
-            best_cost = cost;
-            best_tps = tps;
-        }
-        if (S == 1) break;
-    }
-    p.tps = best_tps;
-    p.S = (p.nt + best_tps - 1) / best_tps;
-    p.units = mt2 * p.S;
-    return p;
-}
-
-static bool use_pair_kernel(int Q) {
-    // EXPERIMENTAL, off by default.  Measured on 10k x 1M (ncu, profiles/r1f_search10k_ctapair_experiment.txt): bit-identical
-    // lists, same tensor-pipe activity (85.6 %), but 48 GB of DRAM reads instead of 7.6 GB (L2 hit rate 78 % vs 96 %, 5x the
-    // die-to-die sectors) and, under the power cap, 1.35 GHz instead of 1.43: 30.3 vs 28.1 ms.  Up to ~5k queries the two
-    // kernels tie.  The single-CTA kernel already reads only ~60 % of the nominal L2->SM bytes (neighbouring CTAs of a TPC
-    // ask for the same database tile), which is the saving the pair was meant to bring.
-    static const char* dbg = getenv("CIR_SEARCH_2CTA");
-    return dbg && dbg[0] == '1' && Q > BM;
-}
-
-static int launch_search2(const void* q, int Q, const void* db, long long N, int Kd, SearchParams& P, const SearchPlan& plan,
-                          cudaStream_t stream) {
-    const DeviceInfo& dev = device_info();
-    CIR_REQUIRE(dev.max_smem_optin >= SMEM2_BYTES, CIR_ERR_UNSUPPORTED, "search: device offers %d B shared memory, need %d",
-                dev.max_smem_optin, SMEM2_BYTES);
-    CUtensorMap tmA, tmBh;
-    int rc = make_tmap(&tmA, q, (uint64_t)Q, (uint64_t)Kd, BM);
-    if (rc) return rc;
-    rc = make_tmap(&tmBh, db, (uint64_t)N, (uint64_t)Kd, BN / 2);
-    if (rc) return rc;
-    P.Q = Q;
-    P.N = (int)N;
-    P.kblocks = Kd / BK;
-    P.mt = plan.mt; P.nt = plan.nt; P.S = plan.S; P.tps = plan.tps; P.units = plan.units; P.Qpad = plan.Qpad;
-    P.b_policy = 0;
-    P.tile_stride = 1;
-    static thread_local int attr_dev = -1;
-    if (attr_dev != dev.device) {
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-        attr_dev = dev.device;
-    }
-    const int npairs = dev.num_sms / 2;
-    const int grid = 2 * (plan.units < npairs ? plan.units : npairs);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(SEARCH_THREADS);
-    cfg.dynamicSmemBytes = SMEM2_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CIR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, search2_kernel, tmA, tmBh, P));
-    count_launch();
-    return CIR_OK;
 }
 
 // N = rows of the problem; the matrix behind `db` has N_map >= N rows and problem tile n is matrix tile n * tile_stride
@@ -850,12 +576,7 @@ extern "C" int cir_search_workspace_bytes(int Q, int64_t N, int Kd, int k, size_
     CIR_REQUIRE(bytes && Q > 0 && N > 0 && k >= 1 && k <= SEARCH_MAX_K, CIR_ERR_INVALID_ARG,
                 "cir_search_workspace_bytes: bad arguments (Q=%d N=%lld k=%d, k <= %d)", Q, (long long)N, k, SEARCH_MAX_K);
     const SearchPlan plan = plan_search(Q, N, device_info().num_sms);
-    size_t total = search_ws_layout(plan, Q, search_cap_for_k(k), sample_rows(Q, N, k)).total;
-    if (use_pair_kernel(Q)) {
-        const size_t t2 = search_ws_layout(plan_search2(Q, N, device_info().num_sms), Q, search_cap_for_k(k), sample_rows(Q, N, k)).total;
-        if (t2 > total) total = t2;
-    }
-    *bytes = total;
+    *bytes = search_ws_layout(plan, Q, search_cap_for_k(k), sample_rows(Q, N, k)).total;
     return CIR_OK;
 }
 
@@ -897,8 +618,7 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
     CIR_REQUIRE(workspace && workspace_bytes >= need, CIR_ERR_WORKSPACE, "cir_search_topk: workspace %zu < %zu bytes",
                 workspace_bytes, need);
     CIR_REQUIRE(((uintptr_t)workspace & 15) == 0, CIR_ERR_INVALID_ARG, "cir_search_topk: workspace must be 16 B aligned");
-    const bool pair = use_pair_kernel(Q) && !q_label;
-    const SearchPlan plan = pair ? plan_search2(Q, N, device_info().num_sms) : plan_search(Q, N, device_info().num_sms);
+    const SearchPlan plan = plan_search(Q, N, device_info().num_sms);
     const int n0_ws = sample_rows(Q, N, k);
     const SearchWs w = search_ws_layout(plan, Q, search_cap_for_k(k), n0_ws);
     char* ws = static_cast<char*>(workspace);
@@ -930,8 +650,7 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
     P.tau0 = tau0;
     P.q_label = q_label;
     P.db_label = db_label;
-    if (pair) rc = launch_search2(q, Q, db, N, Kd, P, plan, static_cast<cudaStream_t>(stream));
-    else rc = launch_search(MODE_TOPK, q, Q, db, N, Kd, P, plan, static_cast<cudaStream_t>(stream));
+    rc = launch_search(MODE_TOPK, q, Q, db, N, Kd, P, plan, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
     return launch_topk_select_lists(P.lists, P.counts, plan.S, plan.Qpad, P.cap, Q, k, out_scores, out_idx, k, idx_offset,
                                     static_cast<cudaStream_t>(stream), peers, n_peers, my_rank);
