@@ -214,6 +214,7 @@ __device__ __forceinline__ float row_reduce(int pm, const float* row, int HW, bo
         CIR_ROW_CASE(PM_MAX)
         CIR_ROW_CASE(PM_MEAN)
         case PM_GENERAL_POLY0 + 1: a = row_partial_vec<PM_GENERAL_POLY0 + 1, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
+        case PM_GENERAL_POLY0 + 2: a = row_partial_vec<PM_GENERAL_POLY0 + 2, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p); break;
         default:
             a = vec ? row_partial_vec<PM_GENERAL, GLOBAL>(reinterpret_cast<const float4*>(row), HW >> 2, lane, eps, p)
                     : row_partial_scalar<PM_GENERAL>(row, HW, lane, eps, p);
@@ -443,8 +444,12 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                 }
             } else {
                 // consumer warps; the consumer count is a compile-time constant in either variant (no runtime modulo)
-                auto consume = [&](auto nc_tag) {
+                // PMC >= 0: one exponent class for every row, known before the loop -- the row arithmetic is inlined and the
+                // loop carries no classification / jump table (those cost ~50 of the ~150 bookkeeping instructions per
+                // row); PMC < 0: per-channel exponents (GeMmp), classified row by row.
+                auto consume = [&](auto nc_tag, auto pm_tag) {
                     constexpr int NC = decltype(nc_tag)::value;
+                    constexpr int PMC = decltype(pm_tag)::value;
                     // this CTA's W tile -> bf16 hi / lo UMMA tiles, spread over the 480 consumer lanes in three
                     // batches of 4 chunks interleaved with the row stream (each batch: 8 loads in flight per lane)
                     constexpr int CONV_BATCHES = (TAIL_W_TASKS + NC * 32 * 4 - 1) / (NC * 32 * 4);
@@ -462,13 +467,17 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     int j = warp % rps;
                     int slot = (warp / rps) % n_slots, bar = (warp / rps) % nbar;
                     uint32_t par = (uint32_t)((warp / rps) / nbar) & 1u;
-                    const int pm_shared = classify_p(P.pool_mode, p_shared, P.gen_mode);
                     for (int i = warp; i < my_rows; i += NC) {
                         mbar_wait(&full_bar[bar], par);
-                        const float pr = (gem && P.p_stride) ? __ldg(P.p + cur_c) : p_shared;
-                        const int pm = (gem && P.p_stride) ? classify_p(P.pool_mode, pr, P.gen_mode) : pm_shared;
                         const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
-                        const float a = row_reduce<false>(pm, src, HW, true, lane, P.eps_gem, pr);
+                        float a;
+                        if constexpr (PMC >= 0) {
+                            a = row_partial_vec<PMC, false>(reinterpret_cast<const float4*>(src), HW >> 2, lane, P.eps_gem, p_shared);
+                            a = PMC == PM_MAX ? warp_max(a) : warp_sum(a);
+                        } else {
+                            const float pr = __ldg(P.p + cur_c);
+                            a = row_reduce<false>(classify_p(P.pool_mode, pr, P.gen_mode), src, HW, true, lane, P.eps_gem, pr);
+                        }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
                         take(a, cur_n, cur_c);
@@ -490,7 +499,21 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, CONV_BATCHES - conv_done);
                     flush();
                 };
-                consume(std::integral_constant<int, TAIL_CONSUMERS>{});
+                using NCt = std::integral_constant<int, TAIL_CONSUMERS>;
+#define CIR_CONSUME(PMV) consume(NCt{}, std::integral_constant<int, PMV>{})
+                if (gem && P.p_stride) CIR_CONSUME(-1);
+                else switch (classify_p(P.pool_mode, p_shared, P.gen_mode)) {
+                    case PM_3: CIR_CONSUME(PM_3); break;
+                    case PM_2: CIR_CONSUME(PM_2); break;
+                    case PM_1: CIR_CONSUME(PM_1); break;
+                    case PM_4: CIR_CONSUME(PM_4); break;
+                    case PM_MAX: CIR_CONSUME(PM_MAX); break;
+                    case PM_MEAN: CIR_CONSUME(PM_MEAN); break;
+                    case PM_GENERAL_POLY0 + 1: CIR_CONSUME(PM_GENERAL_POLY0 + 1); break;
+                    case PM_GENERAL_POLY0 + 2: CIR_CONSUME(PM_GENERAL_POLY0 + 2); break;
+                    default: CIR_CONSUME(PM_GENERAL); break;
+                }
+#undef CIR_CONSUME
             }
         } else {
             if (own_unit) convert_w_tile<2>(P, Bt, blockIdx.x, tid, TAIL_THREADS);
@@ -806,7 +829,7 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
         // non-integer exponent: how many of every 4 ex2 go to the FMA pipe (CIR_TAIL_NPOLY = 0 / 1 for experiments; 2..4
         // were measured and lost, see the comment at fold4)
         static const char* dbg = getenv("CIR_TAIL_NPOLY");
-        const int npoly = (dbg && dbg[0] >= '0' && dbg[0] <= '1') ? dbg[0] - '0' : TAIL_NPOLY_DEFAULT;
+        const int npoly = (dbg && dbg[0] >= '0' && dbg[0] <= '2') ? dbg[0] - '0' : TAIL_NPOLY_DEFAULT;
         P.gen_mode = npoly == 0 ? PM_GENERAL : PM_GENERAL_POLY0 + npoly;
     }
 
