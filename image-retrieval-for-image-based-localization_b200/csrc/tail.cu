@@ -44,7 +44,7 @@ constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 con
 constexpr int TAIL_NT = 128;                         // output dims per projection unit (UMMA N)
 constexpr int TAIL_KS = 256;                         // K slice per projection unit (4 k blocks of 64)
 constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows (phase A) / one 128 x 64 bf16 A tile (phase B)
-constexpr int TAIL_MAX_SLOTS = 14;                   // the whole 224 KB of shared memory as 16 KB slots
+constexpr int TAIL_MAX_SLOTS = 8;
 constexpr int TAIL_MAX_BARS = 32;
 constexpr int TAIL_MB = 128;                         // images per phase-B pass (UMMA M)
 constexpr int TAIL_BT_BYTES = TAIL_NT * 128;         // one B tile: 128 rows x 64 k bf16, 128 B swizzle (16 KB)
@@ -74,10 +74,7 @@ struct TailParams {
     unsigned flags;
     int bulk_ok;       // rows can be moved by cp.async.bulk
     int vec_ok;        // rows are 16 B aligned and HW % 4 == 0
-    int n_slots;       // ring slots behind the W tile (phase B; phase A too when the W tile is converted in place)
-    int n_slots_a;     // phase A ring slots
-    int w_global;      // phase A converts the W tile into `wtiles` (global scratch) and the ring takes ALL shared memory
-    unsigned char* wtiles;   // [units][TAIL_W_BYTES] bf16 hi / lo UMMA tiles, L2-resident
+    int n_slots;       // ring slots
     int w_bytes;       // shared-memory bytes reserved for the W slice
     int gen_mode;      // exponent class of a non-integer p on vector rows: PM_GENERAL or PM_GENERAL_POLY0 + NPOLY
     unsigned long long* stamps;   // optional [gridDim][8] globaltimer stamps (CIR_TAIL_DEBUG_STAMPS)
@@ -313,8 +310,7 @@ __device__ __forceinline__ void convert_w_tile(const TailParams& P, unsigned cha
             }
         }
     }
-    // the tiles are read by the tensor core or, from the global scratch, by a bulk copy (async proxy either way)
-    asm volatile("fence.proxy.async;" ::: "memory");
+    fence_proxy_async();       // the tiles are read by the tensor core (async proxy)
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
@@ -323,12 +319,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     unsigned char* tail_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* Bt = tail_smem;                                                 // W slice as UMMA B tiles (whiten)
     unsigned char* ring = tail_smem + P.w_bytes;                                   // [n_slots][16 KB]
-    // Phase A: with the W tile parked in global memory (w_global) the ring is the whole shared memory -- 14 slots instead of 6.
-    // The 15 rows in work pin four slots; what is left holds the bytes in flight, and two slots (32 KB per SM) were less than
-    // the stream needs whenever the per-row arithmetic is not negligible (non-integer exponent).
-    unsigned char* ringA = P.w_global ? tail_smem : ring;
-    unsigned char* Wdst = P.w_global ? P.wtiles + (size_t)blockIdx.x * TAIL_W_BYTES : Bt;
-    __shared__ __align__(8) uint64_t wbar;                       // W tile back from the global scratch (w_global)
     // Phase A barriers: a ring of nbar = M * n_slots (full, empty) pairs over the n_slots data slots.  A consumer warp
     // only visits the slots that hold its rows, so it does not observe every phase of a barrier; with a single ring a
     // parity wait could then be satisfied by an OLDER, still incomplete phase (bulk copies complete out of order).
@@ -420,7 +410,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
             // Slot size: 16 KB.  Smaller slots pin less of the ring while rows are being reduced, but the stream then moves
             // in smaller bulk copies and collapses (measured at 64 x 2048 x 32 x 32, p = 3: 16 KB slots 98.8 us, 8 KB
             // 120.9 us, 4 KB 204.8 us per launch).
-            const int n_slots = P.n_slots_a;
+            const int n_slots = P.n_slots;
             const int rps = max(1, TAIL_SLOT_BYTES / (HW * 4));              // rows per slot
             const int iters = (my_rows + rps - 1) / rps;
             // gap between two rows of a consumer warp: at most TAIL_CONSUMERS iterations (+1)
@@ -446,7 +436,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         const int nr = min(rps, my_rows - t * rps);
                         const uint32_t bytes = (uint32_t)nr * (uint32_t)HW * 4u;
                         mbar_arrive_expect_tx(&full_bar[bar], bytes);
-                        bulk_load(ringA + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
+                        bulk_load(ring + (size_t)slot * TAIL_SLOT_BYTES, P.x + (r0 + (long long)t * rps) * HW, bytes,
                                   &full_bar[bar], pol);
                         if (++slot == n_slots) slot = 0;
                         if (++bar == nbar) bar = 0;
@@ -479,7 +469,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     uint32_t par = (uint32_t)((warp / rps) / nbar) & 1u;
                     for (int i = warp; i < my_rows; i += NC) {
                         mbar_wait(&full_bar[bar], par);
-                        const float* src = reinterpret_cast<const float*>(ringA + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
+                        const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
                         float a;
                         if constexpr (PMC >= 0) {
                             a = row_partial_vec<PMC, false>(reinterpret_cast<const float4*>(src), HW >> 2, lane, P.eps_gem, p_shared);
@@ -501,12 +491,12 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         par ^= carry ? fl1 : fl0;
                         if (bar >= nbar) { bar -= nbar; par ^= 1u; }
                         if (own_unit && conv_done < CONV_BATCHES && ++taken == (conv_done + 1) * conv_every) {
-                            convert_w_tile<4>(P, Wdst, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, 1);
+                            convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, 1);
                             ++conv_done;
                         }
                     }
                     if (own_unit && conv_done < CONV_BATCHES)      // short streams: whatever is left
-                        convert_w_tile<4>(P, Wdst, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, CONV_BATCHES - conv_done);
+                        convert_w_tile<4>(P, Bt, blockIdx.x, warp * 32 + lane, NC * 32, conv_done, CONV_BATCHES - conv_done);
                     flush();
                 };
                 using NCt = std::integral_constant<int, TAIL_CONSUMERS>;
@@ -542,20 +532,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
     }
     stamp(P, 1);
     if (pool_only) return;
-    const bool w_fetch = own_unit && P.w_global && P.bulk_ok;
-    if (w_fetch) {
-        // every warp is done with the ring and has fenced its W chunks: bring the tile (128 KB, L2-resident) into place
-        // while this CTA waits at the grid barrier anyway
-        __syncthreads();
-        if (tid == 0) {
-            mbar_init(&wbar, 1);
-            fence_barrier_init();
-            mbar_arrive_expect_tx(&wbar, TAIL_W_BYTES);
-            const uint64_t pol = policy_evict_first();
-            for (int i = 0; i < TAIL_W_BYTES / TAIL_SLOT_BYTES; ++i)
-                bulk_load(Bt + (size_t)i * TAIL_SLOT_BYTES, Wdst + (size_t)i * TAIL_SLOT_BYTES, TAIL_SLOT_BYTES, &wbar, pol);
-        }
-    }
 
     // phase-B setup (barriers, TMEM, tensor-map prefetch) does not depend on the pooled vectors: do it before the grid
     // barrier instead of on the critical path behind it
@@ -639,7 +615,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     }
                 } else if (warp == 1) {
                     if (lane == 0) {
-                        if (w_fetch && unit == (int)blockIdx.x && n0 == 0) mbar_wait(&wbar, 0);     // the W tile has landed
                         for (int kb = 0; kb < nkb; ++kb) {
                             const int s_hi = slot;
                             const uint32_t ph_hi = phase;
@@ -818,10 +793,9 @@ using namespace cir;
 
 extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) {
     CIR_REQUIRE(bytes && N > 0 && C > 0 && D_out > 0, CIR_ERR_INVALID_ARG, "cir_tail_workspace_bytes: bad arguments");
-    // pooled [N, C] (fp32, or bf16 hi + lo) + part [ceil(C / 256)][N][D_out] + W tiles [units][128 KB] + debug stamps
+    // pooled [N, C] (fp32, or bf16 hi + lo) + part [ceil(C / 256)][N][D_out] + debug stamps
     const size_t kslices = ((size_t)C + TAIL_KS - 1) / TAIL_KS;
-    const size_t units = kslices * (((size_t)D_out + TAIL_NT - 1) / TAIL_NT);
-    *bytes = align_up((size_t)N * C * 4, 256) + align_up(kslices * (size_t)N * D_out * 4, 256) + units * TAIL_W_BYTES + TAIL_STAMP_BYTES;
+    *bytes = align_up((size_t)N * C * 4, 256) + align_up(kslices * (size_t)N * D_out * 4, 256) + TAIL_STAMP_BYTES;
     return CIR_OK;
 }
 
@@ -885,9 +859,6 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
         P.n_kslices = (C + TAIL_KS - 1) / TAIL_KS;
         P.units = P.n_ntiles * P.n_kslices;
         P.w_bytes = TAIL_W_BYTES;
-        P.wtiles = reinterpret_cast<unsigned char*>(P.part) + align_up((size_t)P.n_kslices * N * D_out * 4, 256);
-        static const char* dbg = getenv("CIR_TAIL_WGLOBAL");          // experiments: "0" converts the W tile in place (r1)
-        P.w_global = P.bulk_ok && !(dbg && dbg[0] == '0');
     }
     // ring: as many 16 KB slots as fit beside the W slice (and at least the phase-B scratch)
     const int static_smem = 2048;     // barriers + reduction scratch (1.5 KB today), with slack
@@ -895,8 +866,6 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     if (slots > TAIL_MAX_SLOTS) slots = TAIL_MAX_SLOTS;
     CIR_REQUIRE(slots >= (whiten ? 2 : 1), CIR_ERR_UNSUPPORTED, "cir_tail_fwd: shared memory");
     P.n_slots = slots;
-    P.n_slots_a = P.w_global ? (slots * TAIL_SLOT_BYTES + P.w_bytes) / TAIL_SLOT_BYTES : slots;
-    if (P.n_slots_a > TAIL_MAX_SLOTS) P.n_slots_a = TAIL_MAX_SLOTS;
     const size_t smem = (size_t)P.w_bytes + (size_t)slots * TAIL_SLOT_BYTES + 1024 /* 1 KB alignment of the tiles */;
     CUtensorMap tmHi, tmLo;
     memset(&tmHi, 0, sizeof(tmHi));

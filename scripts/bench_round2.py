@@ -12,7 +12,7 @@ from cirtorch_b200.utils import whiten as W
 dev = torch.device("cuda:0")
 PK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else \
     {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-what = set(sys.argv[1:]) or {"train", "loss", "whiten", "rank", "regions"}
+what = set(sys.argv[1:]) or {"train", "loss", "whiten", "rank", "regions", "eager"}
 
 
 def timeit(fn, n=10, warm=3):
@@ -97,3 +97,22 @@ if "regions" in what:
     ms = timeit(lambda: LF.region_pool(x, regs, p=p3, pooling="GeM"), n=10)
     print(json.dumps({"what": "region_pool 15 regions, 64x2048x32x32", "ms": ms, "gbs": x.numel() * 4 / (ms * 1e-3) / 1e9,
                       "frac_of_hbm_peak": x.numel() * 4 / (ms * 1e-3) / 1e9 / PK["hbm_gbs"]}))
+if "eager" in what:
+    # the reference's head as stock eager PyTorch ops ON THE B200 (the "unfused GPU" comparison):
+    # clamp / pow / avg_pool2d / pow, norm / div, Linear, norm / div -- pools.py:37-38, normalizations.py:15-16, global_head.py:52-67
+    import torch.nn.functional as F
+    x = torch.relu(torch.randn((64, 2048, 32, 32), device=dev, generator=g))
+    Wt = torch.randn((2048, 2048), device=dev, generator=g) * 0.02
+    b = torch.zeros(2048, device=dev)
+    for p in (3.0, 2.7):
+        pt = torch.ones(1, device=dev) * p
+
+        def eager():
+            v = F.avg_pool2d(x.clamp(min=1e-6).pow(pt), (32, 32)).pow(1.0 / pt)
+            v = (v / (torch.norm(v, p=2, dim=1, keepdim=True) + 1e-6).expand_as(v)).squeeze(-1).squeeze(-1)
+            v = F.linear(v, Wt, b)
+            return (v / (torch.norm(v, p=2, dim=1, keepdim=True) + 1e-6).expand_as(v)).permute(1, 0)
+        with torch.no_grad():
+            ms = timeit(eager, n=20)
+        print(json.dumps({"what": "reference head as eager PyTorch ops on the B200 (unfused), 64x2048x32x32, p=%.1f" % p, "ms": ms,
+                          "gbs_algorithmic": 554_180_608 / (ms * 1e-3) / 1e9}))

@@ -194,3 +194,46 @@ def test_entry_points_validate_before_touching_the_device():
     for name, call in calls.items():
         assert call() == -1, name
         assert name.encode() in lib.cir_last_error(), (name, lib.cir_last_error())
+
+
+def test_ragged_batch_containers():
+    """PackedSequence / pad_packed_images / pack_padded_images (host containers either side of the path): own invariants,
+    and -- where the reference tree is present -- the same results as cirtorch/utils/parallel/packed_sequence.py and
+    cirtorch/utils/sequence.py on random ragged inputs."""
+    import os
+    import sys
+    import pytest
+    import torch
+    from cirtorch_b200.utils.sequence import PackedSequence, pad_packed_images, pack_padded_images
+    g = torch.Generator().manual_seed(0)
+    imgs = [torch.randn(3, h, w, generator=g) for (h, w) in ((5, 7), (9, 4), (6, 6))]
+    seq = PackedSequence(imgs)
+    assert len(seq) == 3 and seq[1] is imgs[1] and not seq.all_none and seq.dtype == torch.float32
+    assert isinstance(seq[0:2], PackedSequence) and len(seq[0:2]) == 2 and len(seq + seq) == 6
+    padded, sizes = pad_packed_images(seq, pad_value=-1.0, snap_size_to=4)
+    assert tuple(padded.shape) == (3, 3, 12, 8) and [tuple(s) for s in sizes] == [(5, 7), (9, 4), (6, 6)]
+    assert float(padded[0, :, 5:, :].max()) == -1.0 and torch.equal(padded[1, :, :9, :4], imgs[1])
+    back = pack_padded_images(padded, sizes)
+    assert all(torch.equal(a, b) for a, b in zip(back, imgs))
+    labels = PackedSequence([torch.tensor([-1., 1., 0.]), None, torch.tensor([-1., 1., 0.])])
+    cat, idx = labels.contiguous
+    assert cat.tolist() == [-1, 1, 0, -1, 1, 0] and idx.tolist() == [0, 0, 0, 2, 2, 2]
+    assert PackedSequence([None, None]).contiguous == (None, None) and PackedSequence([None]).all_none
+    with pytest.raises(ValueError):
+        PackedSequence(imgs).contiguous                      # different spatial sizes: no contiguous view
+    with pytest.raises(TypeError):
+        PackedSequence([torch.zeros(1), torch.zeros(1, dtype=torch.float64)])
+    with pytest.raises(ValueError):
+        pad_packed_images(PackedSequence([None]))
+    if os.path.isdir("/root/reference/cirtorch"):
+        sys.path.insert(0, "/root/reference")
+        from cirtorch.utils.parallel.packed_sequence import PackedSequence as RefSeq
+        from cirtorch.utils.sequence import pad_packed_images as ref_pad
+        for with_none in (False, True):
+            items = list(imgs) + ([None] if with_none else [])
+            a, sa = pad_packed_images(PackedSequence(items), pad_value=0.5, snap_size_to=None)
+            b, sb = ref_pad(RefSeq(items), pad_value=0.5, snap_size_to=None)
+            assert torch.equal(a, b) and [tuple(x) for x in sa] == [tuple(x) for x in sb]
+        ra, rb = RefSeq([torch.ones(2, 3), None, torch.zeros(1, 3)]).contiguous
+        ma, mb = PackedSequence([torch.ones(2, 3), None, torch.zeros(1, 3)]).contiguous
+        assert torch.equal(ra, ma) and torch.equal(rb, mb)
