@@ -17,7 +17,8 @@
 namespace cir {
 
 constexpr int SEL_MAX_PEERS = 16;
-constexpr int SEL_N = 4096;
+constexpr int SEL_N = 4096;          // keys per shared-memory tile of the sorts / re-scoring
+constexpr int SEL_CAP = 8192;        // keys the block-per-query selection holds at once
 constexpr int SEL_THREADS = 512;
 
 // in-place descending bitonic sort of buf[0, P) (P a power of two <= SEL_N); `base` is the
@@ -70,7 +71,7 @@ struct SelParams {
 constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_MAX_KOUT = 1024;    // largest k the select / merge kernel emits
-constexpr int SEL_SMEM_BYTES = SEL_N * 8 + SEL_MAX_KOUT * 8 + SEL_WARPS * 256 * 4 + (2 * SEL_MAX_LISTS + 1 + 8 + 3) * 4;
+constexpr int SEL_SMEM_BYTES = SEL_CAP * 8 + SEL_MAX_KOUT * 8 + SEL_WARPS * 256 * 4 + (2 * SEL_MAX_LISTS + 1 + 8 + 3) * 4;
 
 template <int SRC> __global__ void topk_select_kernel(const struct SelParams p);
 template <int SRC>
@@ -249,8 +250,8 @@ __device__ __forceinline__ int warp_keep_topk(unsigned long long* buf, int n, in
 template <int SRC>
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParams p) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
-    unsigned long long* buf = reinterpret_cast<unsigned long long*>(sel_smem);          // [SEL_N]
-    unsigned long long* stage = buf + SEL_N;                                            // [SEL_MAX_KOUT]
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(sel_smem);          // [SEL_CAP]
+    unsigned long long* stage = buf + SEL_CAP;                                          // [SEL_MAX_KOUT]
     int* hist = reinterpret_cast<int*>(stage + SEL_MAX_KOUT);                            // [SEL_WARPS][256]
     int* s_cnt = hist + SEL_WARPS * 256;      // [SEL_MAX_LISTS] list sizes of the current window of lists
     int* s_off = s_cnt + SEL_MAX_LISTS;       // [SEL_MAX_LISTS + 1] exclusive prefix sums
@@ -282,23 +283,66 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
         __syncthreads();
         int done = 0;     // lists of this window already consumed
         while (done < win) {
-            // take as many lists as fit behind the `fill` survivors of the previous round
-            const int room = SEL_N - fill;
+            // Take as many lists as fit behind the `fill` survivors of the previous round: the largest `take` with
+            // s_off[take] - start <= room, by bisection (every thread used to walk the offsets one by one: 148 lists per
+            // query at 70 queries x 1M -- 15 % of the kernel's samples).  A list always fits: fill <= k and k + cap <= SEL_CAP.
+            const int room = SEL_CAP - fill;
             const int start = s_off[done];
-            int take = done;
-            while (take < win && s_off[take + 1] - start <= room) ++take;    // uniform across threads
-            // warp w copies lists done + w, done + w + 16, ...
-            for (int g = done + warp; g < take; g += SEL_WARPS) {
-                const int c = s_cnt[g];
-                const int dst = fill + s_off[g] - start;
-                if (SRC == 0) {
-                    const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
-                    for (int t = lane; t < c; t += 32) buf[dst + t] = raw_to_key(__ldcg(L + t));
-                } else {
-                    const size_t o = (size_t)(g0 + g) * (size_t)p.g_stride + (size_t)q * p.kin;
-                    for (int t = lane; t < c; t += 32) {
-                        const int32_t ix = __ldg(p.in_idx + o + t);
-                        buf[dst + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+            int take = done, hi = win;
+            while (take < hi) {
+                const int mid = (take + hi + 1) >> 1;
+                if (s_off[mid] - start <= room) take = mid; else hi = mid - 1;
+            }
+            // Gather: warp w copies lists done + w, done + w + 16, ...  The first 64 entries of EIGHT lists are loaded before
+            // any is stored (16 independent global loads in flight per lane); the plain loop had one dependent L2 round
+            // trip per list and query (23 % of the samples of 70 x 1M waited there), a flat gather with a bisection per
+            // entry traded that for 8 x more instructions.  Longer lists finish in a remainder loop.
+            constexpr int LPW = 8;
+            for (int gb = done + warp; gb < take; gb += SEL_WARPS * LPW) {
+                unsigned long long v0[LPW], v1[LPW];
+#pragma unroll
+                for (int u = 0; u < LPW; ++u) {
+                    const int g = gb + u * SEL_WARPS;
+                    v0[u] = v1[u] = 0ull;
+                    if (g < take) {
+                        const int c = s_cnt[g];
+                        if (SRC == 0) {
+                            const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
+                            if (lane < c) v0[u] = __ldcg(L + lane);
+                            if (lane + 32 < c) v1[u] = __ldcg(L + lane + 32);
+                        } else {
+                            const size_t o = (size_t)(g0 + g) * (size_t)p.g_stride + (size_t)q * p.kin;
+                            if (lane < c) {
+                                const int32_t ix = __ldg(p.in_idx + o + lane);
+                                v0[u] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + lane), (uint32_t)ix);
+                            }
+                            if (lane + 32 < c) {
+                                const int32_t ix = __ldg(p.in_idx + o + lane + 32);
+                                v1[u] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + lane + 32), (uint32_t)ix);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < LPW; ++u) {
+                    const int g = gb + u * SEL_WARPS;
+                    if (g < take) {
+                        const int c = s_cnt[g];
+                        const int dst = fill + s_off[g] - start;
+                        if (lane < c) buf[dst + lane] = SRC == 0 ? raw_to_key(v0[u]) : v0[u];
+                        if (lane + 32 < c) buf[dst + lane + 32] = SRC == 0 ? raw_to_key(v1[u]) : v1[u];
+                        if (c > 64) {
+                            if (SRC == 0) {
+                                const unsigned long long* L = p.lists + ((size_t)(g0 + g) * p.Qpad + q) * p.cap;
+                                for (int t = lane + 64; t < c; t += 32) buf[dst + t] = raw_to_key(__ldcg(L + t));
+                            } else {
+                                const size_t o = (size_t)(g0 + g) * (size_t)p.g_stride + (size_t)q * p.kin;
+                                for (int t = lane + 64; t < c; t += 32) {
+                                    const int32_t ix = __ldg(p.in_idx + o + t);
+                                    buf[dst + t] = ix < 0 ? 0ull : make_key(__ldg(p.in_scores + o + t), (uint32_t)ix);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -313,13 +357,23 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
         g0 += win;
         __syncthreads();
     }
-    // final ordering of the <= k survivors
-    const int P = next_pow2(fill);
-    for (int t = fill + tid; t < P; t += SEL_THREADS) buf[t] = 0ull;
+    // Final ordering of the <= k survivors: rank sort.  The keys are distinct (the index is part of the key), so the rank of a
+    // key is the number of larger keys: `fill` broadcast reads per thread and two barriers, where the bitonic network over a
+    // few hundred keys cost log^2 stages of block barriers (28 for k = 100) -- a large part of this kernel's time when it
+    // serves a handful of queries (70 x 1M: 38 us of selection on a 0.6 ms scan, the same on the 78 us scan of an 8-GPU shard).
+    for (int t = tid; t < p.k; t += SEL_THREADS) stage[t] = 0ull;       // empty slots (fewer than k candidates) sort last
     __syncthreads();
-    block_bitonic(buf, P, 0, 2, P, tid, SEL_THREADS);
+    for (int t = tid; t < fill; t += SEL_THREADS) {
+        const unsigned long long key = buf[t];
+        if (key != 0ull) {
+            int rank = 0;
+            for (int u = 0; u < fill; ++u) { const unsigned long long o = buf[u]; rank += (o > key || (o == key && u < t)) ? 1 : 0; }
+            stage[rank] = key;
+        }
+    }
+    __syncthreads();
     for (int t = tid; t < p.k; t += SEL_THREADS) {
-        const unsigned long long key = t < fill ? buf[t] : 0ull;
+        const unsigned long long key = stage[t];
         const bool ok = key != 0ull;
         const float sc = ok ? key_score(key) : -INFINITY;
         const int32_t ix = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
@@ -580,7 +634,7 @@ static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
                              float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream,
                              void* const* peers, int n_peers, int my_rank) {
-    CIR_REQUIRE(k + cap <= SEL_N, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_N);
+    CIR_REQUIRE(k + cap <= SEL_CAP, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_CAP);
     SelParams p{};
     p.lists = lists; p.counts = counts; p.Qpad = Qpad; p.cap = cap;
     p.G = S; p.Q = Q; p.k = k;
@@ -721,8 +775,8 @@ extern "C" int cir_topk_merge(const float* scores, const int32_t* idx, int G, in
                               float* out_scores, int32_t* out_idx, int k_out, void* stream) {
     CIR_REQUIRE(scores && idx && out_scores && out_idx, CIR_ERR_INVALID_ARG, "cir_topk_merge: null pointer");
     CIR_REQUIRE(G >= 1 && Q >= 0 && k >= 1 && k_out >= 1, CIR_ERR_INVALID_ARG, "cir_topk_merge: bad shape");
-    CIR_REQUIRE(k_out + k <= SEL_N && k_out <= SEL_MAX_KOUT, CIR_ERR_UNSUPPORTED,
-                "cir_topk_merge: k_out + k = %d exceeds %d (or k_out > %d)", k_out + k, SEL_N, SEL_MAX_KOUT);
+    CIR_REQUIRE(k_out + k <= SEL_CAP && k_out <= SEL_MAX_KOUT, CIR_ERR_UNSUPPORTED,
+                "cir_topk_merge: k_out + k = %d exceeds %d (or k_out > %d)", k_out + k, SEL_CAP, SEL_MAX_KOUT);
     if (Q == 0) return CIR_OK;
     SelParams p{};
     CIR_REQUIRE(g_stride == 0 || g_stride >= (int64_t)Q * k, CIR_ERR_INVALID_ARG, "cir_topk_merge: g_stride too small");
