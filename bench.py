@@ -34,7 +34,7 @@ import torch
 
 B, C, H, W, DOUT = 64, 2048, 32, 32, 2048
 TAIL_BYTES = B * C * H * W * 4 + DOUT * C * 4 + DOUT * 4 + B * DOUT * 4          # 554,180,608
-TAIL_NCU_TRAFFIC = 553_768_448 + 4_396_288      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r1h_tail.txt)
+TAIL_NCU_TRAFFIC = 553_789_952 + 3_634_688      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r2_tail_p3.txt)
 DB_N, DB_D, TOPK = 1_000_000, 2048, 100
 WORKLOAD = "fused tail: batch 64x2048x32x32 fp32 maps -> GeM(p=3)+L2N+whiten 2048->2048+L2N"
 METRIC = "descriptors/s (GeM+whiten tail) & queries/s vs 1M×2048 DB at 1/2/4/8 B200, %roofline"
@@ -738,7 +738,7 @@ def main():
     gb27 = TAIL_BYTES / (ms27 * 1e-3) / 1e9
     tail_p27 = {"p": 2.7, "ms_per_step": ms27, "descriptors_per_s": world * B / (ms27 * 1e-3),
                 "roofline": {"bound": "hbm", "achieved": gb27, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb27 / pk["hbm_gbs"],
-                             "traffic": None, "note": "general exponent: x^p = ex2(p lg2 x), half of the ex2 on the FMA pipe"}}
+                             "traffic": None, "note": "general exponent: x^p = ex2(p lg2 x), one of every four ex2 on the FMA pipe; same algorithmic bytes"}}
     del head27
 
     # end to end through the module API with HOST buffers: H2D of the maps, the fused tail, D2H of the descriptors
@@ -788,7 +788,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": TAIL_NCU_TRAFFIC,
                          "note": "554,180,608 algorithmic bytes per launch / mean launch time; peak = %s copy bandwidth; "
-                                 "traffic = dram read+write per launch from profiles/r1h_tail.txt" % pk["src"]},
+                                 "traffic = dram read+write per launch from profiles/r2_tail_p3.txt" % pk["src"]},
             "tail_p27": tail_p27, "search": search,
         }
         if not args.no_search:
