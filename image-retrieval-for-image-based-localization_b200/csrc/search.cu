@@ -61,7 +61,7 @@ struct SearchParams {
     float* dense_out;            // MODE_DENSE: [Q, dense_ld]
     long long dense_ld;
     int b_policy;                // database tiles: 0 evict_last, 1 evict_first, 2 evict_normal
-    int tile_stride;             // database tile n of the problem is tile n * tile_stride of the matrix (threshold sample: > 1)
+    long long piece_stride;      // MODE_GROUPMAX: the problem's rows are 32-row pieces of the matrix, piece i at row i * piece_stride
 };
 
 // ---------------------------------------------------------------------------------------
@@ -190,7 +190,16 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         uint8_t* a = smem + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
                         tma_load_2d_hint(a, &tmA, &full[stage], kb * BK, m * BM, pol_a);
-                        tma_load_2d_hint(a + A_BYTES, &tmB, &full[stage], kb * BK, n * P.tile_stride * BN, pol_b);
+                        if (MODE == MODE_GROUPMAX) {
+                            // threshold sample: the 256 rows of a tile are eight 32-row pieces from eight places of the matrix
+                            // (tmB has a 32-row box here); a piece is 4 KB of the swizzled tile, 1 KB aligned
+#pragma unroll
+                            for (int pc = 0; pc < BN / 32; ++pc)
+                                tma_load_2d_hint(a + A_BYTES + pc * 32 * 128, &tmB, &full[stage], kb * BK,
+                                                 (int)(((long long)n * (BN / 32) + pc) * P.piece_stride), pol_b);
+                        } else {
+                            tma_load_2d_hint(a + A_BYTES, &tmB, &full[stage], kb * BK, n * BN, pol_b);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -347,7 +356,7 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         // query's k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.
                         if (valid) {
                             if (LABELS) {                   // mining: rows of the query's own cluster do not count
-                                const int32_t* lab = P.db_label + (long long)n * P.tile_stride * BN + c * 32;   // the sampled tile's rows
+                                const int32_t* lab = P.db_label + ((long long)n * (BN / 32) + c) * P.piece_stride;     // the sampled piece's rows
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
                                     if (__ldg(lab + j) == qlab) v[j] = 0xff800000u;      // -inf
@@ -460,24 +469,24 @@ SearchPlan plan_search(int Q, long long N, int num_sms) {
     return p;
 }
 
-// N = rows of the problem; the matrix behind `db` has N_map >= N rows and problem tile n is matrix tile n * tile_stride
-// (tile_stride > 1: the threshold sample takes tiles spread evenly over the whole matrix)
+// N = rows of the problem; MODE_GROUPMAX (the threshold sample): the matrix behind `db` has N_map >= N rows and the problem's
+// rows are its 32-row pieces i * piece_stride .. + 31 (piece_stride = 32: the first N rows)
 static int launch_search(int mode, const void* q, int Q, const void* db, long long N, int Kd, SearchParams& P,
-                         const SearchPlan& plan, cudaStream_t stream, long long N_map = 0, int tile_stride = 1) {
+                         const SearchPlan& plan, cudaStream_t stream, long long N_map = 0, long long piece_stride = 32) {
     const DeviceInfo& dev = device_info();
     CIR_REQUIRE(dev.max_smem_optin >= SMEM_BYTES, CIR_ERR_UNSUPPORTED, "search: device offers %d B shared memory, need %d",
                 dev.max_smem_optin, SMEM_BYTES);
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, q, (uint64_t)Q, (uint64_t)Kd, BM);
     if (rc) return rc;
-    rc = make_tmap(&tmB, db, (uint64_t)(N_map > N ? N_map : N), (uint64_t)Kd, BN);
+    rc = make_tmap(&tmB, db, (uint64_t)(N_map > N ? N_map : N), (uint64_t)Kd, mode == MODE_GROUPMAX ? 32 : BN);
     if (rc) return rc;
     P.Q = Q;
     P.N = (int)N;
     P.kblocks = Kd / BK;
     P.mt = plan.mt; P.nt = plan.nt; P.S = plan.S; P.tps = plan.tps; P.units = plan.units; P.Qpad = plan.Qpad;
     P.b_policy = plan.mt == 1 ? 1 : 0;
-    P.tile_stride = tile_stride;
+    P.piece_stride = piece_stride;
     static thread_local int attr_dev = -1;
     if (attr_dev != dev.device) {
         CIR_CHECK_CUDA(cudaFuncSetAttribute(search_kernel<MODE_TOPK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -632,11 +641,14 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
         D.dense_ld = n0 / GROUP;
         D.q_label = q_label;          // mining: the threshold only counts rows the query may take
         D.db_label = db_label;
-        // the sample = n0 / 256 tiles spread evenly over the FULL tiles of the matrix, so that the threshold does not depend
-        // on how the rows are ordered (a database stored scene by scene: its first rows are a handful of scenes)
-        const int stride = (flags & CIR_SEARCH_SAMPLE_FIRST_ROWS) ? 1 : (int)((N / BN) / (n0 / BN));
+        // The sample = n0 / 32 pieces of 32 consecutive rows spread evenly over the matrix, so that the threshold does not
+        // depend on how the rows are ordered.  Whole 256-row tiles were not fine enough: on a shard stored centre by
+        // centre (125k rows of an 8-GPU search: a 4,096-row sample = 16 tiles = ~40 distinct centres) the k-th largest
+        // of 512 group maxima was the ~9th best CENTRE, which admitted 20 % of the rows (5.11 vs 3.96 ms).
+        const long long pieces = n0 / 32;
+        const long long stride = (flags & CIR_SEARCH_SAMPLE_FIRST_ROWS) ? 32 : N / pieces;
         rc = launch_search(MODE_GROUPMAX, q, Q, db, n0, Kd, D, plan_search(Q, n0, device_info().num_sms),
-                           static_cast<cudaStream_t>(stream), N, stride < 1 ? 1 : stride);
+                           static_cast<cudaStream_t>(stream), N, stride < 32 ? 32 : stride);
         if (rc) return rc;
         rc = launch_row_kth_largest(dense, Q, n0 / GROUP, n0 / GROUP, k, tau, static_cast<cudaStream_t>(stream));
         if (rc) return rc;

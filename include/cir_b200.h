@@ -51,7 +51,7 @@ extern "C" {
 /* flags of cir_search_topk */
 #define CIR_SEARCH_SORTED 0u      /* (default) lists sorted by (score desc, index asc)  */
 #define CIR_SEARCH_NO_PREPASS 1u  /* skip the threshold warm start (sample of the rows)   */
-#define CIR_SEARCH_SAMPLE_FIRST_ROWS 2u /* threshold sample = the first rows instead of tiles spread over the matrix */
+#define CIR_SEARCH_SAMPLE_FIRST_ROWS 2u /* threshold sample = the first rows instead of 32-row pieces spread over the matrix */
 
 const char* cir_last_error(void);
 int cir_version(void);
