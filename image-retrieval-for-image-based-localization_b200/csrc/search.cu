@@ -263,6 +263,7 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const int col0 = n * BN;
+                float gmax[MODE == MODE_GROUPMAX ? 32 : 1];          // MODE_GROUPMAX: running maxima over the tile's eight pieces
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];
@@ -351,9 +352,12 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                             }
                         }
                     } else if (MODE == MODE_GROUPMAX) {
-                        // threshold pre-pass: only the maximum of every 8 consecutive rows leaves the SM (N % 256 == 0 here).
-                        // Each maximum is the score of a distinct row, so the k-th largest of them is a lower bound of the
-                        // query's k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.
+                        // Threshold pre-pass: of every 8 rows only the maximum leaves the SM (N % 256 == 0 here).  Each
+                        // maximum is the score of a distinct row, so the k-th largest of them is a lower bound of the query's
+                        // k-th best score -- at 1/8 of the bytes and 1/8 of the selection work of the dense block.  A group is
+                        // the SAME offset j in the tile's eight 32-row pieces, i.e. 8 rows from 8 different places of the
+                        // matrix: the maximum of 8 neighbouring rows of a centre-sorted database is hardly an extreme value
+                        // (the rows of a centre score alike), and the bound then admitted 8 x more candidates.
                         if (valid) {
                             if (LABELS) {                   // mining: rows of the query's own cluster do not count
                                 const int32_t* lab = P.db_label + ((long long)n * (BN / 32) + c) * P.piece_stride;     // the sampled piece's rows
@@ -361,16 +365,15 @@ search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                 for (int j = 0; j < 32; ++j)
                                     if (__ldg(lab + j) == qlab) v[j] = 0xff800000u;      // -inf
                             }
-                            float m[32 / GROUP];
 #pragma unroll
-                            for (int g = 0; g < 32 / GROUP; ++g) {
-                                float x = __uint_as_float(v[g * GROUP]);
+                            for (int j = 0; j < 32; ++j)
+                                gmax[j] = c == 0 ? __uint_as_float(v[j]) : fmaxf(gmax[j], __uint_as_float(v[j]));
+                            if (c == BN / 32 - 1) {
+                                float* o = P.dense_out + (long long)qg * P.dense_ld + col0 / GROUP;
 #pragma unroll
-                                for (int j = 1; j < GROUP; ++j) x = fmaxf(x, __uint_as_float(v[g * GROUP + j]));
-                                m[g] = x;
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(o + j) = make_float4(gmax[j], gmax[j + 1], gmax[j + 2], gmax[j + 3]);
                             }
-                            *reinterpret_cast<float4*>(P.dense_out + (long long)qg * P.dense_ld + cb / GROUP) =
-                                make_float4(m[0], m[1], m[2], m[3]);
                         }
                     } else {
                         if (valid) {
