@@ -535,6 +535,10 @@ def bench_extract_rank(dev, rank, world, with_cpu):
     images, backbone, fused tail, D2H / all_gather of the descriptors); ranking = the reference's full N x Q argsort."""
     from cirtorch_b200 import parallel as P, search as S
     from cirtorch_b200.extract import resnet50_gem, extract_vectors
+    try:          # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the image staging
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // world))
+    except AttributeError:
+        pass
     torch.manual_seed(0)
     net = resnet50_gem().to(dev).eval()
     n_img = 32 * world

@@ -87,26 +87,43 @@ def extract_vectors(net, images, image_size=1024, transform=None, bbxs=None, ms=
     zero-padded to Hmax x Wmax (cirtorch/utils/sequence.py:4-67) and GeM pools over the padding, because
     ``globalFeatureAlgo.inference`` ignores the valid sizes (GF_algo.py:85-90).
     """
-    device = device or next(net.parameters()).device
+    device = torch.device(device) if device is not None else next(net.parameters()).device
     net.eval()
     n = len(images)
     lo, hi = (rank * n) // world_size, ((rank + 1) * n) // world_size
     D = net.ret_head.dim
     vecs = torch.zeros(D, hi - lo, device=device)
+    # equal-sized images are stacked straight into one of two pinned staging buffers and copied asynchronously: the host
+    # side of a batch (stack + H2D) then overlaps the backbone of the previous one
+    stage, staged = [None, None], [None, None]
+    turn = 0
     i = lo
     while i < hi:
         j = min(hi, i + batch_size)
         items = [_load(images[t], image_size, transform, None if bbxs is None else bbxs[t]) for t in range(i, j)]
         shapes = {tuple(t.shape) for t in items}
         if len(shapes) == 1:
-            groups = [(list(range(i, j)), torch.stack(items))]
+            shape = (batch_size,) + tuple(items[0].shape)
+            if device.type == "cuda" and not items[0].is_cuda and items[0].dtype == torch.float32:
+                if stage[turn] is None or tuple(stage[turn].shape) != shape:
+                    stage[turn] = torch.empty(shape, dtype=torch.float32).pin_memory()
+                elif staged[turn] is not None:
+                    staged[turn].synchronize()          # the copy that last read this buffer has finished
+                torch.stack(items, out=stage[turn][:len(items)])
+                batch = stage[turn][:len(items)].to(device, non_blocking=True)
+                staged[turn] = torch.cuda.Event()
+                staged[turn].record()
+                turn ^= 1
+            else:
+                batch = torch.stack(items).to(device, non_blocking=True)
+            groups = [(list(range(i, j)), batch)]
         elif pad_ragged:                       # the fork's behaviour: one zero-padded batch
             from .utils.sequence import PackedSequence, pad_packed_images
-            groups = [(list(range(i, j)), pad_packed_images(PackedSequence(items))[0])]
+            groups = [(list(range(i, j)), pad_packed_images(PackedSequence(items))[0].to(device, non_blocking=True))]
         else:                                  # ragged sizes: one launch per image
-            groups = [([i + t], it[None]) for t, it in enumerate(items)]
+            groups = [([i + t], it[None].to(device, non_blocking=True)) for t, it in enumerate(items)]
         for ids, batch in groups:
-            out = net(batch.to(device, non_blocking=True), scales=tuple(ms))
+            out = net(batch, scales=tuple(ms))
             vecs[:, ids[0] - lo:ids[-1] - lo + 1] = out
         i = j
     return vecs.cpu() if world_size == 1 else vecs
