@@ -3,23 +3,22 @@
 // Replaces cirtorch/modules/pools.py:37-38, normalizations.py:15-16 and
 // heads/global_head.py:52-67 (seven eager PyTorch ops, three full passes over the map)
 // with ONE cooperative launch of one 512-thread CTA per SM:
-//   phase A  the HBM stream.  Warp 15 is a producer: one thread feeds a ring of 16 KB
-//            shared-memory slots with cp.async.bulk (TMA bulk copies of whole (n, c) rows,
-//            L2 evict-first) completing on mbarriers; warps 0..14 consume rows from shared
-//            memory (clamp, x^p, sum / max; warp-shuffle reduce) and finish 32 rows at a
-//            time (mean^(1/p)) -> pooled[n, c] (N*C floats, stays in L2).  The bytes in
-//            flight are the ring, not registers.  Meanwhile the CTA's slice of W (<= 16
-//            output rows, <= 128 KB) is prefetched into shared memory with cp.async.
+//   phase A  the HBM stream.  Warp 15 is a producer: one thread feeds a ring of 16 KB shared-memory slots with
+//            cp.async.bulk (TMA bulk copies of whole (n, c) rows, L2 evict-first) completing on mbarriers; warps 0..14
+//            consume rows from shared memory (clamp, x^p, sum / max; warp-shuffle reduce) and finish 32 rows at a time
+//            (mean^(1/p)).  The bytes in flight are the ring, not registers.  The consumer loop is instantiated per
+//            exponent class (p = 1, 2, 3, 4, general, max, mean), so its body is the inlined arithmetic; the (image,
+//            channel) of a row is tracked incrementally.  Between rows the 480 consumer lanes convert this CTA's W tile
+//            (128 output dims x 256 k, fp32, read from HBM once) into bf16 hi / lo UMMA tiles in shared memory (128 KB).
 //            Rows that TMA cannot move (H*W % 4 != 0, > 16 KB, unaligned) take a direct-load path.
+//            Phase A stores the pooled vectors already split into bf16 hi + lo parts (and, on request, as fp32 for the
+//            backward pass).
 //   barrier  cooperative grid sync
-//            Phase A stores the pooled vectors already split into bf16 hi + lo parts.
 //   phase B  split-K projection on tcgen05: unit (nt, ks) = 128 output dims x a 256-wide K slice;
 //            part[ks][n][nt*128 ..] = G[128 images x 256] . W_tile^T with every fp32 operand split into
 //            hi + lo bf16 (hi.hi + hi.lo + lo.hi, fp32 accumulator in TMEM: ~1e-5 relative, inside
 //            the 1e-4 bar).  A CTA reads only ITS K slice of the pooled vectors (64 KB by TMA, 128 B
-//            swizzle) instead of all of them; its W tile (128 KB as bf16 hi / lo UMMA tiles) was
-//            converted during phase A by the idle lanes of the producer warp.  Warp 0 TMA, warp 1
-//            MMA issue, warp 2 TMEM alloc, warps 8-11 epilogue (tcgen05.ld -> partial sums).
+//            swizzle).  Warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 8-11 epilogue (tcgen05.ld -> partial sums).
 //   barrier  cooperative grid sync
 //   phase C  one CTA per image: adds the K-slice partial sums in a fixed order (deterministic), applies
 //            the first L2N as a scale (||g|| from the pooled vector), the bias and the second L2N.
