@@ -54,7 +54,7 @@ extern "C" {
 #define CIR_SEARCH_SAMPLE_FIRST_ROWS 2u /* threshold sample = the first rows instead of 32-row pieces spread over the matrix */
 
 const char* cir_last_error(void);
-int cir_version(void);
+int cir_version(void);            /* 100 = round 1, 200 = round 2 (cir_tail_fwd gained pooled_out; section 7 added) */
 /* number of kernels launched by this library on the calling thread since the last reset
  * (bench.py's gpu_launches counter) */
 int64_t cir_launch_count(int reset);
