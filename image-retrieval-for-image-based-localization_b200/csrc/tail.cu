@@ -684,29 +684,36 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
 
     // ------------------------------------------------------------------ phase C: one CTA per image
     {
-        __shared__ float redc[TAIL_WARPS];
-        __shared__ float bcast;
-        auto block_sum = [&](float v) -> float {       // deterministic: fixed shuffle tree, then warps in order
+        __shared__ float redc[2][TAIL_WARPS];
+        // deterministic block sum: fixed shuffle tree, then every thread adds the 16 warp sums in order (ONE barrier; the
+        // two sums of an image use different scratch rows, a third use waits for the loop's trailing barrier)
+        auto block_sum = [&](float v, int which) -> float {
             v = warp_sum(v);
+            if (lane == 0) redc[which][warp] = v;
             __syncthreads();
-            if (lane == 0) redc[warp] = v;
-            __syncthreads();
-            if (tid == 0) {
-                float t = 0.0f;
+            float t = 0.0f;
 #pragma unroll
-                for (int w = 0; w < TAIL_WARPS; ++w) t += redc[w];
-                bcast = t;
-            }
-            __syncthreads();
-            return bcast;
+            for (int w = 0; w < TAIL_WARPS; ++w) t += redc[which][w];
+            return t;
         };
         for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
-            // issue everything that does not depend on a reduction first: the K-slice partial sums (fixed order)
+            // issue everything that does not depend on a reduction first, so that ONE L2 round trip covers it all: the pooled
+            // vector (first L2N), the bias, then the K-slice partial sums (fixed order)
             constexpr int YR = 8;
-            float yreg[YR];
+            float yreg[YR], breg[YR];
             const bool in_regs = P.D_out <= YR * TAIL_THREADS;
+            uint4 gh = make_uint4(0, 0, 0, 0), gl = gh;
+            const int c_first = tid * 8;
+            if (c_first < P.C) {
+                gh = __ldcg(reinterpret_cast<const uint4*>(P.pooled_hi + (size_t)n * P.C + c_first));
+                gl = __ldcg(reinterpret_cast<const uint4*>(P.pooled_lo + (size_t)n * P.C + c_first));
+            }
 #pragma unroll
-            for (int i = 0; i < YR; ++i) yreg[i] = 0.0f;
+            for (int i = 0; i < YR; ++i) {
+                const int d = tid + i * TAIL_THREADS;
+                yreg[i] = 0.0f;
+                breg[i] = (P.bias && d < P.D_out) ? __ldg(P.bias + d) : 0.0f;
+            }
             // 4 slices x 8 dims = up to 32 independent L2 loads in flight per thread, added in slice order (an
             // accumulate-as-you-load loop serialised 32 L2 latencies: ~6 us on the critical path)
             for (int ks0 = 0; ks0 < P.n_kslices; ks0 += 4) {
@@ -725,17 +732,17 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                     for (int i = 0; i < YR; ++i) yreg[i] += t[u][i];
             }
             // first L2N: ||g_n|| from the split pooled vector
-            float sg = 0.0f;
-            for (int c = tid * 8; c < P.C; c += TAIL_THREADS * 8)
+            float sg = c_first < P.C ? sumsq8(gh, gl) : 0.0f;
+            for (int c = c_first + TAIL_THREADS * 8; c < P.C; c += TAIL_THREADS * 8)
                 sg += sumsq8(__ldcg(reinterpret_cast<const uint4*>(P.pooled_hi + (size_t)n * P.C + c)),
                              __ldcg(reinterpret_cast<const uint4*>(P.pooled_lo + (size_t)n * P.C + c)));
-            const float inv = 1.0f / (sqrtf(block_sum(sg)) + P.eps_l2);     // W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
+            const float inv = 1.0f / (sqrtf(block_sum(sg, 0)) + P.eps_l2);     // W.(g/(|g|+eps)) == (W.g)/(|g|+eps)
             float sy = 0.0f;
 #pragma unroll
             for (int i = 0; i < YR; ++i) {
                 const int d = tid + i * TAIL_THREADS;
                 if (d < P.D_out) {
-                    yreg[i] = yreg[i] * inv + (P.bias ? __ldg(P.bias + d) : 0.0f);
+                    yreg[i] = yreg[i] * inv + breg[i];
                     sy = fmaf(yreg[i], yreg[i], sy);
                 }
             }
@@ -745,7 +752,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                 const float y = acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f);
                 sy = fmaf(y, y, sy);
             }
-            const float denom = sqrtf(block_sum(sy)) + P.eps_l2;
+            const float denom = sqrtf(block_sum(sy, 1)) + P.eps_l2;
 #pragma unroll
             for (int i = 0; i < YR; ++i) {
                 const int d = tid + i * TAIL_THREADS;
