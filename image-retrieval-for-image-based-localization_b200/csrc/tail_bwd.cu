@@ -15,11 +15,21 @@ template <int PI>   // PI = integer exponent 1..4, 0 = general
 __device__ __forceinline__ void gem_bwd_elem(float x, float eps, float p, float coef, bool want_s, float& dx, float& s) {
     const float t = fmaxf(x, eps);
     float tpm1;     // t^(p-1)
+    if (PI == 0) {
+        // general exponent: ONE lg2 serves both t^(p-1) = ex2((p-1) lg2 t) and ln t = lg2 t * ln 2 (two MUFU per element; the
+        // libm-style exp2f / logf pair cost ~3x the instructions and made the general backward 0.13 ms slower than p = 3)
+        float l, e;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(t));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((p - 1.0f) * l));
+        tpm1 = e;
+        dx = x >= eps ? coef * tpm1 : 0.0f;
+        if (want_s) s = fmaf(tpm1 * t, l * 0.6931471805599453f, s);
+        return;
+    }
     if (PI == 1) tpm1 = 1.0f;
     else if (PI == 2) tpm1 = t;
     else if (PI == 3) tpm1 = t * t;
-    else if (PI == 4) tpm1 = t * t * t;
-    else tpm1 = exp2f((p - 1.0f) * __log2f(t));
+    else tpm1 = t * t * t;
     dx = x >= eps ? coef * tpm1 : 0.0f;
     if (want_s) s = fmaf(tpm1 * t, __logf(t), s);
 }
