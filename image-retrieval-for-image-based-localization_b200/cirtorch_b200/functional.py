@@ -177,8 +177,10 @@ class _TailFn(torch.autograd.Function):
                     lib = _lib.load()
                     pc = p.detach().reshape(-1).float().contiguous()
                     dp = torch.empty_like(pc)
+                    ws = _lib.workspace(g.device, g.shape[0] * 4 + 64, "gem_dp")
                     rc = lib.cir_gem_dp(_lib.ptr(g), _lib.ptr(dg), _lib.ptr(S), _lib.ptr(pc), 0 if pc.numel() == 1 else 1,
-                                        g.shape[0], g.shape[1], x.shape[2] * x.shape[3], _lib.ptr(dp), _lib.stream_of(g))
+                                        g.shape[0], g.shape[1], x.shape[2] * x.shape[3], _lib.ptr(dp), _lib.ptr(ws), ws.numel(),
+                                        _lib.stream_of(g))
                     _lib.check(rc, "cir_gem_dp")
                     dp = dp.reshape(p.shape)
         return dx, dp, dW, db, None, None, None, None

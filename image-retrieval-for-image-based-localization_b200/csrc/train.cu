@@ -133,28 +133,34 @@ tuple_loss_kernel(const float* __restrict__ x, long long ldx, int n_tuples, int 
     }
 }
 
-// out[n, :] = gout / (s + eps) - v (v . gout) / (s (s + eps)^2),  s = ||v[n, :]||;  one warp per row.
+// out[n, :] = gout / (s + eps) - v (v . gout) / (s (s + eps)^2),  s = ||v[n, :]||;  one 256-thread block per row (a batch
+// has 64 .. 448 rows: a warp per row left 8 blocks on 148 SMs and 16 us per call).
 // unit_out (optional) = v / (s + eps): the forward value, needed by the caller for dL/dW.
 __global__ void __launch_bounds__(256)
 l2n_bwd_rows_kernel(const float* __restrict__ v, const float* __restrict__ gout, long long N, int C, float eps,
                     float* __restrict__ out, float* __restrict__ unit_out) {
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= N) return;
+    __shared__ float red[2][8];
+    const long long row = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* a = v + row * C;
     const float* g = gout ? gout + row * C : nullptr;
     float ss = 0.0f, dot = 0.0f;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = threadIdx.x; c < C; c += 256) {
         const float x = a[c];
         ss = fmaf(x, x, ss);
         if (g) dot = fmaf(x, g[c], dot);
     }
     ss = warp_sum(ss);
     dot = warp_sum(dot);
+    if (lane == 0) { red[0][warp] = ss; red[1][warp] = dot; }
+    __syncthreads();
+    ss = 0.0f; dot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ss += red[0][w]; dot += red[1][w]; }      // fixed order: deterministic
     const float s = sqrtf(ss);
     const float inv = 1.0f / (s + eps);
     const float k = s > 0.0f ? dot / (s * (s + eps) * (s + eps)) : 0.0f;
-    for (int c = lane; c < C; c += 32) {
+    for (int c = threadIdx.x; c < C; c += 256) {
         const float x = a[c];
         if (out) out[row * C + c] = g[c] * inv - x * k;
         if (unit_out) unit_out[row * C + c] = x * inv;
@@ -173,36 +179,51 @@ colsum_rows_kernel(const float* __restrict__ X, long long N, int C, float* __res
 
 // dL/dp of GeM (autograd of pools.py:37-38):  g = (mean t^p)^(1/p), t = max(x, eps), S = sum_hw t^p ln t
 //   d g / d p = g * ( -ln g / p + S / (p HW g^p) ),   dL/dp = sum dg * dg/dp
-// p_stride 0: one exponent -> out[0] (one block, fixed order); p_stride 1: one per channel -> out[c].
-__global__ void __launch_bounds__(1024)
+// p_stride 1: one exponent per channel -> out[c], one thread per channel.  p_stride 0: one exponent -> out[0]: one block per
+// image sums its C terms, the last block to finish adds the per-image partials in image order (deterministic).  (The first
+// version summed all N*C terms in ONE block: 165 us of a 600 us training step.)
+__device__ __forceinline__ float gem_dp_term(float gv, float dgv, float Sv, float pp, float HW) {
+    if (!(gv > 0.0f)) return 0.0f;
+    float l, gp;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(gv));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(gp) : "f"(pp * l));          // g^p
+    return dgv * gv * (-(l * 0.6931471805599453f) / pp + Sv / (pp * HW * gp));
+}
+
+__global__ void __launch_bounds__(256)
 gem_dp_kernel(const float* __restrict__ g, const float* __restrict__ dg, const float* __restrict__ S, const float* __restrict__ p,
-              int p_stride, int N, int C, float HW, float* __restrict__ out) {
-    auto term = [&](int n, int c, float pp) -> float {
-        const float gv = g[(size_t)n * C + c];
-        if (!(gv > 0.0f)) return 0.0f;
-        const float gp = powf(gv, pp);
-        return dg[(size_t)n * C + c] * gv * (-logf(gv) / pp + S[(size_t)n * C + c] / (pp * HW * gp));
-    };
+              int p_stride, int N, int C, float HW, float* __restrict__ out, float* __restrict__ partial, unsigned* __restrict__ counter) {
     if (p_stride) {
         const int c = blockIdx.x * blockDim.x + threadIdx.x;
         if (c >= C) return;
         const float pp = p[c];
         float acc = 0.0f;
-        for (int n = 0; n < N; ++n) acc += term(n, c, pp);
+        for (int n = 0; n < N; ++n) acc += gem_dp_term(g[(size_t)n * C + c], dg[(size_t)n * C + c], S[(size_t)n * C + c], pp, HW);
         out[c] = acc;
         return;
     }
-    __shared__ float red[32];
+    __shared__ float red[8];
+    __shared__ bool s_last;
+    const int n = blockIdx.x;
     const float pp = p[0];
     float acc = 0.0f;
-    for (int i = threadIdx.x; i < N * C; i += blockDim.x) acc += term(i / C, i % C, pp);
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) acc += gem_dp_term(g[(size_t)n * C + c], dg[(size_t)n * C + c], S[(size_t)n * C + c], pp, HW);
+    acc = block_sum_256(acc, red);
     if (threadIdx.x == 0) {
+        partial[n] = acc;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == (unsigned)(N - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
         float t = 0.0f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-        out[0] = t;
+        for (int i = threadIdx.x; i < N; i += 256) t += __ldcg(partial + i);
+        t = block_sum_256(t, red);
+        if (threadIdx.x == 0) {
+            out[0] = t;
+            *counter = 0u;
+        }
     }
 }
 
@@ -241,7 +262,8 @@ extern "C" int cir_l2n_bwd_rows(const float* v, const float* gout, int64_t N, in
                                 void* stream) {
     CIR_REQUIRE(v && N >= 0 && C > 0 && (out || unit_out) && (!out || gout), CIR_ERR_INVALID_ARG, "cir_l2n_bwd_rows: bad arguments");
     if (N == 0) return CIR_OK;
-    l2n_bwd_rows_kernel<<<(unsigned)((N + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, gout, N, C, eps, out, unit_out);
+    CIR_REQUIRE(N <= 0x7fffffffll, CIR_ERR_UNSUPPORTED, "cir_l2n_bwd_rows: too many rows");
+    l2n_bwd_rows_kernel<<<(unsigned)N, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, gout, N, C, eps, out, unit_out);
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;
@@ -256,12 +278,21 @@ extern "C" int cir_colsum_rows(const float* X, int64_t N, int C, float* out, voi
 }
 
 extern "C" int cir_gem_dp(const float* g, const float* dg, const float* S, const float* p, int p_stride, int N, int C, int HW,
-                          float* out, void* stream) {
+                          float* out, void* workspace, size_t workspace_bytes, void* stream) {
     CIR_REQUIRE(g && dg && S && p && out && N > 0 && C > 0 && HW > 0 && (p_stride == 0 || p_stride == 1), CIR_ERR_INVALID_ARG,
                 "cir_gem_dp: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p_stride) gem_dp_kernel<<<(C + 255) / 256, 256, 0, st>>>(g, dg, S, p, 1, N, C, (float)HW, out);
-    else gem_dp_kernel<<<1, 1024, 0, st>>>(g, dg, S, p, 0, N, C, (float)HW, out);
+    if (p_stride) {
+        gem_dp_kernel<<<(C + 255) / 256, 256, 0, st>>>(g, dg, S, p, 1, N, C, (float)HW, out, nullptr, nullptr);
+    } else {
+        const size_t need = align_up((size_t)N * 4, 16) + 16;          // per-image partial sums + the arrival counter
+        CIR_REQUIRE(workspace && workspace_bytes >= need, CIR_ERR_WORKSPACE, "cir_gem_dp: workspace %zu < %zu bytes (N * 4 + 32)",
+                    workspace_bytes, need);
+        float* partial = static_cast<float*>(workspace);
+        unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + align_up((size_t)N * 4, 16));
+        CIR_CHECK_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+        gem_dp_kernel<<<N, 256, 0, st>>>(g, dg, S, p, 0, N, C, (float)HW, out, partial, counter);
+    }
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;

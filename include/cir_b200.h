@@ -258,7 +258,7 @@ int cir_l2n_bwd_rows(const float* v, const float* gout, int64_t N, int C, float 
                      void* stream);
 int cir_colsum_rows(const float* X, int64_t N, int C, float* out, void* stream);
 int cir_gem_dp(const float* g, const float* dg, const float* S, const float* p, int p_stride, int N, int C, int HW,
-               float* out, void* stream);
+               float* out, void* workspace /* >= N * 4 + 32 bytes, needed for p_stride 0 */, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
