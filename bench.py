@@ -506,11 +506,16 @@ def bench_mining(dev, world, pk, with_cpu):
     n = 10
     ms = timed_region(lambda: M.mine_hard_negatives_rows(qd, pd, qc, pc, 5), n, 3, world) / n
     launches = _lib.launch_count() // (n + 4)
+    ms_bf16 = timed_region(lambda: M.mine_hard_negatives_rows(qd, pd, qc, pc, 5, mode="bf16"), n, 3, world) / n
+    same = bool(torch.equal(M.mine_hard_negatives_rows(qd, pd, qc, pc, 5, mode="bf16")[0], M.mine_hard_negatives_rows(qd, pd, qc, pc, 5)[0]))
     flop = 2.0 * q.shape[0] * pool.shape[0] * DB_D
     tf = flop / (ms * 1e-3) / 1e12
     gb = (q.numel() + pool.numel()) * 4 / (ms * 1e-3) / 1e9
     res = {"ms": ms, "queries_per_s": q.shape[0] / (ms * 1e-3), "Q": q.shape[0], "pool": pool.shape[0], "nnum": 5,
-           "launches": launches, "scaling": "replicas (every rank mines the same epoch; SURVEY.md 8e: multi-GPU optional)",
+           "launches": launches, "ms_mode_bf16": ms_bf16, "mode_bf16_same_sets": same,
+           "mode_note": "default mode bf16x3 (scan error ~1e-5, 80 candidates); mode bf16 = a third of the scan flops, 128 candidates, "
+                        "margin from the rigorous bf16 rounding bound",
+           "scaling": "replicas (every rank mines the same epoch; SURVEY.md 8e: multi-GPU optional)",
            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
                         "hbm_frac": gb / pk["hbm_gbs"], "traffic": None,
                         "note": "latency-bound: 2*Q*P*D = 1.64e11 algorithmic flop (executed 3x as bf16x3) and 180 MB of fp32 inputs over "

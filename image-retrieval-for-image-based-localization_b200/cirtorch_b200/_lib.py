@@ -55,7 +55,8 @@ SIGNATURES = {
     "cir_l2n_bwd_rows": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_f, _vp, _vp, _vp]),
     "cir_colsum_rows": (_c_int, [_vp, _c_i64, _c_int, _vp, _vp]),
     "cir_gem_dp": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, C.c_size_t, _vp]),
-    "cir_mine_filter": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp]),
+    "cir_mine_filter": (_c_int, [_vp, _c_int, _c_int, _vp, _c_i64, _vp, _c_int, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_f,
+                                 _vp, _vp]),
 }
 
 CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC = 0, 1, 2

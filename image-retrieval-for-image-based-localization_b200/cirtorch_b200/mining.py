@@ -17,8 +17,11 @@ from . import _lib
 from . import search as S
 
 
-def mine_filter(cand, pool_cluster, q_cluster, nnum, q_rows=None, pool_rows=None):
-    """Greedy cluster-exclusion walk (cir_mine_filter) -> (sel [Q, nnum] pool positions, count [Q], dist [Q, nnum])."""
+def mine_filter(cand, pool_cluster, q_cluster, nnum, q_rows=None, pool_rows=None, cand_scores=None, scan_tail=None, margin=0.0):
+    """Greedy cluster-exclusion walk (cir_mine_filter) -> (sel [Q, nnum] pool positions, count [Q], dist [Q, nnum], open [Q]).
+
+    ``cand_scores`` [Q, Kc] (exact scores of ``cand``) and ``scan_tail`` [Q] (the scan's score of the list's last entry)
+    switch on the exactness check: ``open[q]`` = 1 where the walk is not conclusive (see mine_hard_negatives_rows)."""
     lib = _lib.load()
     cand = cand.to(torch.int32).contiguous()
     Q, Kc = cand.shape
@@ -26,15 +29,25 @@ def mine_filter(cand, pool_cluster, q_cluster, nnum, q_rows=None, pool_rows=None
     sel = torch.empty((Q, nnum), dtype=torch.int32, device=dev)
     cnt = torch.empty((Q,), dtype=torch.int32, device=dev)
     dist = torch.zeros((Q, nnum), dtype=torch.float32, device=dev)
+    open_ = None
+    if cand_scores is not None:
+        cand_scores = cand_scores.float().contiguous()
+        scan_tail = scan_tail.float().contiguous()
+        open_ = torch.empty((Q,), dtype=torch.int32, device=dev)
     D = 0 if q_rows is None else q_rows.shape[1]
     rc = lib.cir_mine_filter(_lib.ptr(cand), Q, Kc, _lib.ptr(pool_cluster), pool_cluster.shape[0], _lib.ptr(q_cluster),
                              nnum, _lib.ptr(q_rows), _lib.ptr(pool_rows), D, _lib.ptr(sel), _lib.ptr(cnt),
-                             _lib.ptr(dist), _lib.stream_of(cand))
+                             _lib.ptr(dist), _lib.ptr(cand_scores), _lib.ptr(scan_tail), float(margin), _lib.ptr(open_),
+                             _lib.stream_of(cand))
     _lib.check(rc, "cir_mine_filter")
-    return sel, cnt, dist
+    return sel, cnt, dist, open_
 
 
-TOL = {"bf16x3": 2e-5, "bf16": 5e-4}      # |scan score - fp32 score| on unit-norm descriptors
+# |scan score - fp32 score| for descriptors of norm <= 1 (what the head produces).  bf16x3: measured <= 1e-5 (DESIGN.md
+# section 5).  bf16: the RIGOROUS bound 2^-8 (every factor carries a relative rounding error <= 2^-9, Cauchy-Schwarz), not the
+# ~3e-4 seen in practice -- the walk's margin test must never pass wrongly.
+TOL = {"bf16x3": 2e-5, "bf16": 2.0 ** -8}
+KC_DEFAULT = {"bf16x3": 80, "bf16": 128}   # candidates per query of the first pass (bf16: 1/3 of the scan flops, a longer fp32 re-score)
 
 
 def _full_ranking_fp32(sub_q, pool_rows):
@@ -56,7 +69,10 @@ def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num
 
     Returns (sel [Q, neg_num] int32 pool positions best-first, count [Q], dist [Q, neg_num] = ||q - n + 1e-6||_2).
 
-    Exactness.  The candidates of a query are its kc best pool rows by the bf16x3 scan (own cluster masked), re-ordered by
+    ``mode``: "bf16x3" (default; scan error ~1e-5, 80 candidates) or "bf16" (a third of the scan's flops, 128 candidates and
+    a wider margin from the rigorous rounding bound: 0.65 vs 0.81 ms at 2,000 x 20,000 x 2048, same sets).
+
+    Exactness.  The candidates of a query are its kc best pool rows by the scan (own cluster masked), re-ordered by
     exact fp32 scores.  The walk over them is conclusive only if (a) it found neg_num negatives and (b) the fp32 score of
     the LAST negative taken clears the scan score of the kc-th candidate by 2 * TOL[mode] -- otherwise a row just outside
     the list could outrank the walk's tail -- or the list already holds every row the query may take.  Anything else is
@@ -68,7 +84,7 @@ def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num
     P = pool_rows.shape[0]
     q_cluster = q_cluster.to(device=q_rows.device, dtype=torch.int32).contiguous()
     pool_cluster = pool_cluster.to(device=q_rows.device, dtype=torch.int32).contiguous()
-    kc = kc or min(S.MAX_K, max(64, 16 * neg_num))
+    kc = kc or min(S.MAX_K, max(KC_DEFAULT[mode], 16 * neg_num))
     qp = S.pack_rows(q_rows, "query", mode)
     pp = S.pack_rows(pool_rows, "db", mode)
     sel = cnt = dist = None
@@ -79,13 +95,10 @@ def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num
         sub_qc = q_cluster if todo is None else q_cluster[todo].contiguous()
         kk = min(kc, S.MAX_K)
         s3, cand = S.search_packed(sub_qp, pp, kk, q_label=sub_qc, db_label=pool_cluster)
-        _, cand = S.rescore_rows(sub_q, pool_rows, cand, kk)          # exact fp32 order
-        s2, c2, d2 = mine_filter(cand, pool_cluster, sub_qc, neg_num, sub_q, pool_rows)
-        # margin of the last negative taken over the first row that did NOT make the list
-        last = pool_rows[s2[:, neg_num - 1].clamp_min(0).long()]
-        t_last = (sub_q * last).sum(dim=1)
-        complete = torch.isinf(s3[:, kk - 1])                          # fewer than kk rows qualify: nothing is outside the list
-        open_ = ~complete & ((c2 < neg_num) | (t_last - s3[:, kk - 1] < 2 * TOL[mode]))
+        sc, cand = S.rescore_rows(sub_q, pool_rows, cand, kk)         # exact fp32 order
+        # the margin of the last negative taken over the first row that did NOT make the list is checked in the walk kernel
+        s2, c2, d2, open_ = mine_filter(cand, pool_cluster, sub_qc, neg_num, sub_q, pool_rows, cand_scores=sc,
+                                        scan_tail=s3[:, kk - 1], margin=2 * TOL[mode])
         if todo is None:
             sel, cnt, dist = s2, c2, d2
         else:
@@ -98,7 +111,7 @@ def mine_hard_negatives_rows(q_rows, pool_rows, q_cluster, pool_cluster, neg_num
             sub_q = q_rows[todo].contiguous()
             sub_qc = q_cluster[todo].contiguous()
             order = _full_ranking_fp32(sub_q, pool_rows)
-            s2, c2, d2 = mine_filter(order, pool_cluster, sub_qc, neg_num, sub_q, pool_rows)
+            s2, c2, d2, _ = mine_filter(order, pool_cluster, sub_qc, neg_num, sub_q, pool_rows)
             sel[todo], cnt[todo], dist[todo] = s2, c2, d2
             break
         kc = min(S.MAX_K, kc * 4)

@@ -118,12 +118,13 @@ __global__ void __launch_bounds__(128)
 mine_filter_kernel(const int32_t* __restrict__ cand, int Q, int Kc, const int32_t* __restrict__ pool_cluster, long long P,
                    const int32_t* __restrict__ q_cluster, int nnum, const float* __restrict__ q32,
                    const float* __restrict__ pool32, int D, int32_t* __restrict__ out_sel, int32_t* __restrict__ out_count,
-                   float* __restrict__ out_dist) {
+                   float* __restrict__ out_dist, const float* __restrict__ cand_score, const float* __restrict__ scan_tail,
+                   float margin, int32_t* __restrict__ out_open) {
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= Q) return;
     int taken_cluster[MINE_MAX_NNUM];
-    int count = 0;
+    int count = 0, last_pos = -1;
     const int qc = __ldg(q_cluster + q);
     const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(q32) | reinterpret_cast<uintptr_t>(pool32)) & 15) == 0;
     // 32 candidates and their clusters are fetched at once (one lane each); the greedy walk itself then runs on
@@ -141,6 +142,7 @@ mine_filter_kernel(const int32_t* __restrict__ cand, int Q, int Kc, const int32_
             for (int u = 0; u < count; ++u) clash |= taken_cluster[u] == c;
             if (clash) continue;
             taken_cluster[count] = c;
+            last_pos = r0 + t;
             if (lane == 0) out_sel[(size_t)q * nnum + count] = j;
             if (q32 && pool32 && out_dist) {
                 const float* a = q32 + (size_t)q * D;
@@ -170,6 +172,16 @@ mine_filter_kernel(const int32_t* __restrict__ cand, int Q, int Kc, const int32_
     }
     if (lane == 0) {
         out_count[q] = count;
+        if (out_open) {
+            // Is the walk conclusive?  The list is the best Kc rows of an approximate scan, re-ordered by exact scores: a row
+            // just outside it could outrank the walk's tail unless the exact score of the last negative taken clears the
+            // scan score of the list's last entry by `margin` (-inf there = every row the query may take is in the list).
+            const float tail = scan_tail ? __ldg(scan_tail + q) : -INFINITY;
+            bool open = false;
+            if (tail > -INFINITY)
+                open = count < nnum || last_pos < 0 || !cand_score || __ldg(cand_score + (size_t)q * Kc + last_pos) - tail < margin;
+            out_open[q] = open ? 1 : 0;
+        }
         for (int t = count; t < nnum; ++t) {
             out_sel[(size_t)q * nnum + t] = -1;
             if (out_dist) out_dist[(size_t)q * nnum + t] = 0.0f;
@@ -249,13 +261,15 @@ extern "C" int cir_qe_aggregate(const float* q32, int Q, const float* db32, int6
 
 extern "C" int cir_mine_filter(const int32_t* cand, int Q, int Kc, const int32_t* pool_cluster, int64_t P,
                                const int32_t* q_cluster, int nnum, const float* q32, const float* pool32, int D,
-                               int32_t* out_sel, int32_t* out_count, float* out_dist, void* stream) {
+                               int32_t* out_sel, int32_t* out_count, float* out_dist, const float* cand_score,
+                               const float* scan_tail, float margin, int32_t* out_open, void* stream) {
     CIR_REQUIRE(cand && pool_cluster && q_cluster && out_sel && out_count, CIR_ERR_INVALID_ARG, "cir_mine_filter: null pointer");
     CIR_REQUIRE(Q >= 0 && Kc >= 1 && P > 0 && nnum >= 1 && nnum <= MINE_MAX_NNUM, CIR_ERR_INVALID_ARG,
                 "cir_mine_filter: bad shape (nnum <= %d)", MINE_MAX_NNUM);
     if (Q == 0) return CIR_OK;
     mine_filter_kernel<<<(Q + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(cand, Q, Kc, pool_cluster, P, q_cluster, nnum,
-                                                                                   q32, pool32, D, out_sel, out_count, out_dist);
+                                                                                   q32, pool32, D, out_sel, out_count, out_dist,
+                                                                                   cand_score, scan_tail, margin, out_open);
     CIR_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CIR_OK;

@@ -211,11 +211,16 @@ int cir_qe_aggregate(const float* q32, int Q, const float* db32, int64_t N, int 
  *    candidate iff its cluster differs from the query's cluster and from every cluster
  *    already taken; stop at nnum.  out_sel [Q, nnum] pool positions (-1 if exhausted),
  *    out_count [Q] = number taken, out_dist [Q, nnum] = || q - n + 1e-6 ||_2 (:342).
+ *    Optional exactness check (all four or none): cand_score [Q, Kc] = exact scores of the candidates, scan_tail [Q] = the
+ *    approximate scan's score of the list's last entry (-inf if the list holds every admissible row); out_open[q] = 1 if
+ *    the walk found fewer than nnum negatives or the exact score of the last one taken does not clear scan_tail by
+ *    `margin` -- such a query must be re-run with a longer list.
  * ------------------------------------------------------------------------------------ */
 int cir_mine_filter(const int32_t* cand, int Q, int Kc,
                     const int32_t* pool_cluster, int64_t P, const int32_t* q_cluster,
                     int nnum, const float* q32, const float* pool32, int D,
-                    int32_t* out_sel, int32_t* out_count, float* out_dist, void* stream);
+                    int32_t* out_sel, int32_t* out_count, float* out_dist,
+                    const float* cand_score, const float* scan_tail, float margin, int32_t* out_open, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * 6. Evaluation of ranked lists (the consumer of the ranking step)

@@ -188,7 +188,7 @@ def test_entry_points_validate_before_touching_the_device():
         "cir_topk_merge": lambda: lib.cir_topk_merge(None, None, 2, 4, 5, 0, None, None, 5, None),
         "cir_rescore_topk": lambda: lib.cir_rescore_topk(None, 1, None, 10, 8, None, 4, 0, None, None, 2, None),
         "cir_qe_aggregate": lambda: lib.cir_qe_aggregate(None, 1, None, 10, 8, None, None, 4, 4, 2, 3.0, -1, 1e-6, None, None),
-        "cir_mine_filter": lambda: lib.cir_mine_filter(None, 1, 4, None, 10, None, 2, None, None, 8, None, None, None, None),
+        "cir_mine_filter": lambda: lib.cir_mine_filter(None, 1, 4, None, 10, None, 2, None, None, 8, None, None, None, None, None, 0.0, None, None),
         "cir_eval_ap": lambda: lib.cir_eval_ap(None, 1, 4, 4, None, None, None, None, None, 0, None, None, None),
     }
     for name, call in calls.items():
