@@ -426,6 +426,17 @@ def bench_search(dev, rank, world, pk, steps, warmup, state):
                                           "rank reads the final lists back; fp32 re-score of 128 candidates"}
             if name == "q10k" and world > 1:
                 state["parity"].update(parity_search(sh, q32, qp, dev, world, use_p2p))
+            if name == "q70" and use_p2p:
+                # the small batch goes through the fused exchange + merge (arrival counters, no barrier): against NCCL + merge
+                s_l, i_l = step_local()
+                s_all, i_all = P.gather_topk(s_l.clone(), i_l.clone())
+                s_n, i_n = S.merge_topk(s_all, i_all, TOPK)
+                ok = True
+                for _ in range(4):
+                    s_p, i_p = sh.search_packed_p2p(qp, TOPK)
+                    ok = ok and bool(torch.equal(i_p, i_n)) and bool(torch.equal(s_p, s_n))
+                state["parity"]["search_q70_fused_merge_equals_nccl"] = _all_true(ok, dev)
+                res["exchange"] = "peer stores + arrival counters + merge, all inside the selection kernel (symmetric memory; no barrier)"
             out[name] = res
             del q32, qp
         if kind == "iid":

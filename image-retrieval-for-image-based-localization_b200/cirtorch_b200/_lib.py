@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcir_b200.so")
+# CIR_LIB_PATH: an A/B build of the same ABI (experiments); the product is the in-tree library
+LIB_PATH = os.environ.get("CIR_LIB_PATH") or os.path.join(_HERE, "libcir_b200.so")
 
 _c_int = C.c_int
 _c_i64 = C.c_int64
@@ -41,6 +42,8 @@ SIGNATURES = {
                                  C.c_int32, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_search_topk_exchange": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, C.c_int32, C.POINTER(C.c_void_p), _c_int,
                                           _c_int, _vp, C.c_size_t, C.c_uint, _vp]),
+    "cir_search_topk_exchange_merge": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _c_int, C.c_int32, C.POINTER(C.c_void_p), _c_int,
+                                                _c_int, C.c_uint32, _vp, _vp, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_scores_dense": (_c_int, [_vp, _c_int, _vp, _c_i64, _c_int, _vp, _c_i64, _vp]),
     "cir_sort_rows_workspace_bytes": (_c_int, [_c_int, _c_i64, _szp]),
     "cir_sort_rows_desc": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, C.c_size_t, _vp]),

@@ -53,10 +53,12 @@ def gather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None, both: torch
 class PeerExchange:
     """NVLink exchange buffers for the fused search + all-gather (cir_search_topk_exchange).
 
-    Two symmetric-memory buffers [G][2][Q][k] (int32 words) per rank, used alternately: the final selection kernel of
-    every rank stores its lists straight into slot `rank` of all peers' buffers; one device-side barrier later every
-    rank merges its own buffer.  Double buffering makes the single barrier per search sufficient (a rank can only
-    reach the barrier of search i+1 after it launched the merge of search i)."""
+    Two symmetric-memory buffers per rank, used alternately: [G][2][Q][k] int32 words of lists followed by Q arrival
+    counters.  The final selection kernel of every rank stores its lists straight into slot `rank` of all peers' buffers.
+    Small query batches (Q <= the number of SMs): the same kernel then signals the peers' counters, waits on its own and
+    merges (cir_search_topk_exchange_merge) -- no barrier, no merge launch.  Larger batches: one device-side barrier, then
+    every rank merges its own buffer.  Double buffering makes one synchronisation per search sufficient (a rank can only
+    get to search i+1's exchange after every peer's list of search i reached it, i.e. after every peer finished search i-1)."""
 
     def __init__(self, Q: int, k: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -65,18 +67,29 @@ class PeerExchange:
         self.Q, self.k = Q, k
         self.bufs, self.handles, self.ptrs = [], [], []
         import ctypes as C
+        words = self.world_size * 2 * Q * k
+        self.uses = [0, 0]
+        self._flat = []
         for _ in range(2):
-            t = symm_mem.empty((self.world_size, 2, Q, k), dtype=torch.int32, device=device)
-            h = symm_mem.rendezvous(t, self.group)
-            self.bufs.append(t)
+            flat = symm_mem.empty((words + Q,), dtype=torch.int32, device=device)
+            flat[words:].zero_()                                           # the arrival counters start at 0 and only grow
+            h = symm_mem.rendezvous(flat, self.group)
+            self._flat.append(flat)
+            self.bufs.append(flat[:words].view(self.world_size, 2, Q, k))
             self.handles.append(h)
             self.ptrs.append((C.c_void_p * self.world_size)(*[int(a) for a in h.buffer_ptrs]))
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)        # no peer signals a counter before everybody has zeroed theirs
         self.turn = 0
 
-    def next(self):
+    def next(self, fused_merge: bool):
+        """The buffer of this search: (lists view, handle, peer pointers, arrival count its counters reach when every rank
+        has delivered -- only searches with the fused merge signal them)."""
         i = self.turn
         self.turn ^= 1
-        return self.bufs[i], self.handles[i], self.ptrs[i]
+        if fused_merge:
+            self.uses[i] += 1
+        return self.bufs[i], self.handles[i], self.ptrs[i], self.uses[i] * self.world_size
 
 
 class ShardedIndex:
@@ -120,9 +133,11 @@ class ShardedIndex:
         s_all, i_all = gather_topk(s2, i2, self.group)
         return merge_topk(s_all, i_all, k)
 
-    def search_packed_p2p(self, qp, k):
+    def search_packed_p2p(self, qp, k, fused_merge=None):
         """Global top-k of packed queries with the exchange fused into the search: every rank's selection kernel
-        writes its lists into all peers' buffers over NVLink, one device barrier, local merge.  No NCCL call."""
+        writes its lists into all peers' buffers over NVLink.  No NCCL call.  Up to one query per SM the merge is fused in
+        too (arrival counters in the exchange buffers; ``fused_merge=False`` forces the other path); larger batches:
+        one device barrier, then a merge launch."""
         import ctypes as C
         from . import _lib
         from .search import merge_topk
@@ -132,10 +147,20 @@ class ShardedIndex:
         ex = self._exchange.get(key)
         if ex is None:
             ex = self._exchange[key] = PeerExchange(Q, k, qp.device, self.group)
-        buf, handle, ptrs = ex.next()
+        if fused_merge is None:
+            fused_merge = Q <= torch.cuda.get_device_properties(qp.device).multi_processor_count and self.world_size * k <= 8192
+        buf, handle, ptrs, arrivals = ex.next(fused_merge)
         need = C.c_size_t(0)
         _lib.check(lib.cir_search_workspace_bytes(Q, self.index.N, Kd, k, C.byref(need)), "cir_search_workspace_bytes")
         ws = _lib.workspace(qp.device, need.value, "search")
+        if fused_merge:
+            scores = torch.empty((Q, k), dtype=torch.float32, device=qp.device)
+            idx = torch.empty((Q, k), dtype=torch.int32, device=qp.device)
+            rc = lib.cir_search_topk_exchange_merge(_lib.ptr(qp), Q, _lib.ptr(self.index.packed), self.index.N, Kd, k, self.lo,
+                                                    ptrs, self.world_size, self.rank, arrivals, _lib.ptr(scores), _lib.ptr(idx),
+                                                    _lib.ptr(ws), ws.numel(), 0, _lib.stream_of(qp))
+            _lib.check(rc, "cir_search_topk_exchange_merge")
+            return scores, idx
         rc = lib.cir_search_topk_exchange(_lib.ptr(qp), Q, _lib.ptr(self.index.packed), self.index.N, Kd, k, self.lo,
                                           ptrs, self.world_size, self.rank, _lib.ptr(ws), ws.numel(), 0,
                                           _lib.stream_of(qp))

@@ -595,7 +595,7 @@ extern "C" int cir_search_workspace_bytes(int Q, int64_t N, int Kd, int k, size_
 static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int Kd, int k, const float* tau0,
                             const int32_t* q_label, const int32_t* db_label, float* out_scores, int32_t* out_idx,
                             int32_t idx_offset, void* workspace, size_t workspace_bytes, unsigned flags, void* stream,
-                            void* const* peers, int n_peers, int my_rank);
+                            void* const* peers, int n_peers, int my_rank, uint32_t flag_target = 0);
 
 extern "C" int cir_search_topk(const void* q, int Q, const void* db, int64_t N, int Kd, int k, const float* tau0,
                                const int32_t* q_label, const int32_t* db_label, float* out_scores, int32_t* out_idx,
@@ -616,10 +616,22 @@ extern "C" int cir_search_topk_exchange(const void* q, int Q, const void* db, in
                             workspace_bytes, flags, stream, peer_bufs, n_peers, my_rank);
 }
 
+extern "C" int cir_search_topk_exchange_merge(const void* q, int Q, const void* db, int64_t N, int Kd, int k, int32_t idx_offset,
+                                              void* const* peer_bufs, int n_peers, int my_rank, uint32_t arrivals,
+                                              float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                                              unsigned flags, void* stream) {
+    CIR_REQUIRE(peer_bufs && n_peers >= 1 && my_rank >= 0 && my_rank < n_peers && arrivals != 0 && out_scores && out_idx,
+                CIR_ERR_INVALID_ARG, "cir_search_topk_exchange_merge: bad peer arguments");
+    for (int g = 0; g < n_peers; ++g)
+        CIR_REQUIRE(peer_bufs[g], CIR_ERR_INVALID_ARG, "cir_search_topk_exchange_merge: null peer buffer");
+    return search_topk_impl(q, Q, db, N, Kd, k, nullptr, nullptr, nullptr, out_scores, out_idx, idx_offset, workspace,
+                            workspace_bytes, flags, stream, peer_bufs, n_peers, my_rank, arrivals);
+}
+
 static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int Kd, int k, const float* tau0,
                             const int32_t* q_label, const int32_t* db_label, float* out_scores, int32_t* out_idx,
                             int32_t idx_offset, void* workspace, size_t workspace_bytes, unsigned flags, void* stream,
-                            void* const* peers, int n_peers, int my_rank) {
+                            void* const* peers, int n_peers, int my_rank, uint32_t flag_target) {
     int rc = check_operands("cir_search_topk", q, Q, db, N, Kd);
     if (rc) return rc;
     CIR_REQUIRE(k >= 1 && k <= SEARCH_MAX_K, CIR_ERR_UNSUPPORTED, "cir_search_topk: k=%d outside [1, %d]", k, SEARCH_MAX_K);
@@ -668,7 +680,7 @@ static int search_topk_impl(const void* q, int Q, const void* db, int64_t N, int
     rc = launch_search(MODE_TOPK, q, Q, db, N, Kd, P, plan, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
     return launch_topk_select_lists(P.lists, P.counts, plan.S, plan.Qpad, P.cap, Q, k, out_scores, out_idx, k, idx_offset,
-                                    static_cast<cudaStream_t>(stream), peers, n_peers, my_rank);
+                                    static_cast<cudaStream_t>(stream), peers, n_peers, my_rank, flag_target);
 }
 
 extern "C" int cir_scores_dense(const void* q, int Q, const void* db, int64_t N, int Kd, float* out, int64_t ld_out,

@@ -21,7 +21,7 @@ int search_cap_for_k(int k);       // per-(split, query) candidate list capacity
 // final reduction of the candidate lists [S][Qpad][cap] (+ counts [S][Qpad]) to sorted top-k
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
                              float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream,
-                             void* const* peers = nullptr, int n_peers = 0, int my_rank = 0);
+                             void* const* peers = nullptr, int n_peers = 0, int my_rank = 0, uint32_t flag_target = 0);
 
 // tau0[q] = k-th largest of scores[q, 0:n) (n * 4 + 32 KB of shared memory per block)
 int launch_row_kth_largest(const float* scores, int Q, int n, long long ld, int k, float* out, cudaStream_t stream);

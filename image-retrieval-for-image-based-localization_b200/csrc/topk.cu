@@ -66,7 +66,19 @@ struct SelParams {
     // scores then indices of rank g) through NVLink-mapped pointers -- an all-gather without a separate collective
     int n_peers, my_rank;
     void* peer[SEL_MAX_PEERS];
+    // fused merge (flag_target != 0; block-per-query kernel, every block resident): behind the lists every exchange buffer
+    // holds one arrival counter per query.  After its stores the block adds 1 to counter q of every peer (release, system
+    // scope), waits until its own counter reaches flag_target (= uses of this buffer so far x n_peers: the counters are
+    // never reset) and merges the n_peers lists of its query itself -- no cross-GPU barrier, no merge launch.  The merged
+    // lists go to out_scores / out_idx (the local lists are then not written there).
+    uint32_t flag_target;
 };
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int SEL_MAX_LISTS = 1024;   // lists per query handled with shared-memory prefix sums
 constexpr int SEL_WARPS = SEL_THREADS / 32;
@@ -361,31 +373,74 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
     // key is the number of larger keys: `fill` broadcast reads per thread and two barriers, where the bitonic network over a
     // few hundred keys cost log^2 stages of block barriers (28 for k = 100) -- a large part of this kernel's time when it
     // serves a handful of queries (70 x 1M: 38 us of selection on a 0.6 ms scan, the same on the 78 us scan of an 8-GPU shard).
-    for (int t = tid; t < p.k; t += SEL_THREADS) stage[t] = 0ull;       // empty slots (fewer than k candidates) sort last
-    __syncthreads();
-    for (int t = tid; t < fill; t += SEL_THREADS) {
-        const unsigned long long key = buf[t];
-        if (key != 0ull) {
-            int rank = 0;
-            for (int u = 0; u < fill; ++u) { const unsigned long long o = buf[u]; rank += (o > key || (o == key && u < t)) ? 1 : 0; }
-            stage[rank] = key;
+    const bool fused_merge = SRC == 0 && p.flag_target != 0u;
+    for (int round = 0; round < (fused_merge ? 2 : 1); ++round) {
+        for (int t = tid; t < p.k; t += SEL_THREADS) stage[t] = 0ull;       // empty slots (fewer than k candidates) sort last
+        __syncthreads();
+        for (int t = tid; t < fill; t += SEL_THREADS) {
+            const unsigned long long key = buf[t];
+            if (key != 0ull) {
+                int rank = 0;
+                for (int u = 0; u < fill; ++u) { const unsigned long long o = buf[u]; rank += (o > key || (o == key && u < t)) ? 1 : 0; }
+                stage[rank] = key;
+            }
         }
-    }
-    __syncthreads();
-    for (int t = tid; t < p.k; t += SEL_THREADS) {
-        const unsigned long long key = stage[t];
-        const bool ok = key != 0ull;
-        const float sc = ok ? key_score(key) : -INFINITY;
-        const int32_t ix = ok ? (int32_t)key_index(key) + p.idx_offset : -1;
-        if (p.out_scores) {
-            p.out_scores[(size_t)q * p.out_ld + t] = sc;
-            p.out_idx[(size_t)q * p.out_ld + t] = ix;
+        __syncthreads();
+        // round 0: this rank's list (indices + idx_offset); round 1 of a fused merge: the merged list (indices already global)
+        const int32_t add = round == 0 ? p.idx_offset : 0;
+        const bool to_out = p.out_scores && (!fused_merge || round == 1);
+        for (int t = tid; t < p.k; t += SEL_THREADS) {
+            const unsigned long long key = stage[t];
+            const bool ok = key != 0ull;
+            const float sc = ok ? key_score(key) : -INFINITY;
+            const int32_t ix = ok ? (int32_t)key_index(key) + add : -1;
+            if (to_out) {
+                p.out_scores[(size_t)q * p.out_ld + t] = sc;
+                p.out_idx[(size_t)q * p.out_ld + t] = ix;
+            }
+            if (round == 0) {
+                for (int g = 0; g < p.n_peers; ++g) {
+                    // peer buffer layout [G][2][Q][k]; this rank fills slot my_rank of every peer (plain stores over NVLink)
+                    uint32_t* base = static_cast<uint32_t*>(p.peer[g]) + (size_t)p.my_rank * 2 * p.Q * p.k;
+                    base[(size_t)q * p.k + t] = __float_as_uint(sc);
+                    base[(size_t)p.Q * p.k + (size_t)q * p.k + t] = (uint32_t)ix;
+                }
+            }
         }
-        for (int g = 0; g < p.n_peers; ++g) {
-            // peer buffer layout [G][2][Q][k]; this rank fills slot my_rank of every peer (plain stores over NVLink)
-            uint32_t* base = static_cast<uint32_t*>(p.peer[g]) + (size_t)p.my_rank * 2 * p.Q * p.k;
-            base[(size_t)q * p.k + t] = __float_as_uint(sc);
-            base[(size_t)p.Q * p.k + (size_t)q * p.k + t] = (uint32_t)ix;
+        if (!fused_merge || round == 1) break;
+        // ---- arrival counters: signal every peer, wait for all of them, gather the n_peers lists of this query
+        const size_t list_words = (size_t)p.n_peers * 2 * p.Q * p.k;
+        __syncthreads();                                       // every store of this block is issued ...
+        if (tid < p.n_peers) {
+            __threadfence_system();                            // ... and ordered before the signal (cumulative over the barrier)
+            uint32_t* f = static_cast<uint32_t*>(p.peer[tid]) + list_words + q;
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+        }
+        if (tid == 0) {
+            const uint32_t* f = static_cast<const uint32_t*>(p.peer[p.my_rank]) + list_words + q;
+            const uint64_t t0 = global_timer_ns();
+            for (;;) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if ((int32_t)(v - p.flag_target) >= 0) break;
+                if (global_timer_ns() - t0 > 4000000000ull) __trap();      // a peer never arrived (4 s): fail loudly, do not hang
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        const uint32_t* mine = static_cast<const uint32_t*>(p.peer[p.my_rank]);
+        fill = p.n_peers * p.k;
+        for (int t = tid; t < fill; t += SEL_THREADS) {
+            const int g = t / p.k, j = t - g * p.k;
+            const uint32_t* L = mine + (size_t)g * 2 * p.Q * p.k + (size_t)q * p.k + j;
+            const uint32_t sc = __ldcg(L);                                   // written by peers: L2, never a stale L1 line
+            const int32_t ix = (int32_t)__ldcg(L + (size_t)p.Q * p.k);
+            buf[t] = ix < 0 ? 0ull : make_key(__uint_as_float(sc), (uint32_t)ix);
+        }
+        __syncthreads();
+        if (fill > p.k) {
+            block_keep_topk(buf, fill, p.k, hist, stage, s_misc, tid);
+            fill = p.k;
         }
     }
 }
@@ -619,7 +674,7 @@ static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
     int WN = 512;
     while (WN < p.k + longest) WN <<= 1;
     static const char* dbg = getenv("CIR_DEBUG_SELECT");              // experiments: "block" / "warp"
-    const bool want_warp = dbg ? dbg[0] == 'w' : Q >= 4 * dev.num_sms;
+    const bool want_warp = p.flag_target ? false : (dbg ? dbg[0] == 'w' : Q >= 4 * dev.num_sms);
     if (WN <= WSEL_MAX_WN && want_warp) {
         const size_t smem = (size_t)WSEL_WARPS * ((size_t)WN * 8 + 1024);
         topk_select_warp_kernel<SRC><<<(Q + WSEL_WARPS - 1) / WSEL_WARPS, WSEL_WARPS * 32, smem, stream>>>(p, WN);
@@ -633,8 +688,13 @@ static int launch_select(const SelParams& p, int Q, cudaStream_t stream) {
 
 int launch_topk_select_lists(const unsigned long long* lists, const int* counts, int S, int Qpad, int cap, int Q, int k,
                              float* out_scores, int32_t* out_idx, int out_ld, int32_t idx_offset, cudaStream_t stream,
-                             void* const* peers, int n_peers, int my_rank) {
+                             void* const* peers, int n_peers, int my_rank, uint32_t flag_target) {
     CIR_REQUIRE(k + cap <= SEL_CAP, CIR_ERR_UNSUPPORTED, "topk select: k + cap = %d exceeds %d", k + cap, SEL_CAP);
+    if (flag_target) {
+        // every block spins on its peers: all Q blocks must be resident at once (one per SM is always possible)
+        CIR_REQUIRE(n_peers >= 1 && Q <= device_info().num_sms && n_peers * k <= SEL_CAP && out_scores && out_idx, CIR_ERR_UNSUPPORTED,
+                    "topk select: the fused merge needs Q <= %d queries, n_peers * k <= %d and an output", device_info().num_sms, SEL_CAP);
+    }
     SelParams p{};
     p.lists = lists; p.counts = counts; p.Qpad = Qpad; p.cap = cap;
     p.G = S; p.Q = Q; p.k = k;
@@ -642,6 +702,7 @@ int launch_topk_select_lists(const unsigned long long* lists, const int* counts,
     CIR_REQUIRE(n_peers >= 0 && n_peers <= SEL_MAX_PEERS, CIR_ERR_UNSUPPORTED, "topk select: at most %d peers", SEL_MAX_PEERS);
     p.n_peers = n_peers; p.my_rank = my_rank;
     for (int g = 0; g < n_peers; ++g) p.peer[g] = peers[g];
+    p.flag_target = flag_target;
     return launch_select<0>(p, Q, stream);
 }
 

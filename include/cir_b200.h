@@ -162,6 +162,18 @@ int cir_search_topk_exchange(const void* q, int Q, const void* db, int64_t N, in
                              void* const* peer_bufs, int n_peers, int my_rank,
                              void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
+/* The same with the merge fused in as well (Q <= the number of SMs, n_peers * k <= 8192): every exchange buffer is
+ * [n_peers][2][Q][k] int32 words of lists followed by Q 32-bit arrival counters (zeroed once, never reset).  The block that
+ * finishes query q stores its list into every peer's buffer, adds 1 to counter q of every peer (release, system scope), waits
+ * until its OWN counter q reaches `arrivals` (= n_peers x the number of searches that have used this buffer, this one
+ * included) and merges the n_peers lists itself: out_scores / out_idx [Q, k] receive the GLOBAL top-k on every rank.  No
+ * cross-GPU barrier and no merge launch; alternate two buffers between consecutive searches.  Every rank must make the
+ * matching call (a peer that never arrives traps the kernel after 4 s instead of hanging). */
+int cir_search_topk_exchange_merge(const void* q, int Q, const void* db, int64_t N, int Kd, int k, int32_t idx_offset,
+                                   void* const* peer_bufs, int n_peers, int my_rank, uint32_t arrivals,
+                                   float* out_scores, int32_t* out_idx,
+                                   void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
 /* dense scores through the same GEMM (the reference's full `scores` matrix, for full
  * ranking of small databases): out [Q, ld_out] fp32, out[q, n] = q . db[n] */
 int cir_scores_dense(const void* q, int Q, const void* db, int64_t N, int Kd,

@@ -41,6 +41,14 @@ def _worker(rank, world, port, out):
     for _ in range(3):                                               # alternates the two exchange buffers
         s2, i2 = sh.search_packed_p2p(qp, k)                         # fused peer-store exchange
         ok = ok and bool(torch.equal(i2, i_ref)) and bool(torch.equal(s2, s_ref))
+    # a small batch (one block per query, all resident): exchange AND merge inside the selection kernel -- arrival counters
+    # in the exchange buffers instead of a barrier.  One rank is held back on purpose: the other one waits inside its kernel.
+    qp70 = S.pack_rows(q[:70].contiguous(), "query", "bf16")
+    for it in range(6):
+        if it % 2 == rank:
+            torch.cuda._sleep(30_000_000)                            # ~15 ms
+        s4, i4 = sh.search_packed_p2p(qp70, k, fused_merge=(it != 3))   # one search through the barrier path in between
+        ok = ok and bool(torch.equal(i4, i_ref[:70])) and bool(torch.equal(s4, s_ref[:70]))
     # config 5 on shards: alpha-QE with the neighbour sum split over the ranks, DBA with each rank augmenting its rows
     from cirtorch_b200 import rerank as R
     full_index = S.Index(db, mode="bf16")
