@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(const SelParam
                 uint32_t v;
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
                 if ((int32_t)(v - p.flag_target) >= 0) break;
-                if (global_timer_ns() - t0 > 4000000000ull) __trap();      // a peer never arrived (4 s): fail loudly, do not hang
+                if (global_timer_ns() - t0 > 60000000000ull) __trap();     // a peer never arrived (60 s): fail loudly, do not hang
                 __nanosleep(64);
             }
         }

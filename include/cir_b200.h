@@ -168,7 +168,7 @@ int cir_search_topk_exchange(const void* q, int Q, const void* db, int64_t N, in
  * until its OWN counter q reaches `arrivals` (= n_peers x the number of searches that have used this buffer, this one
  * included) and merges the n_peers lists itself: out_scores / out_idx [Q, k] receive the GLOBAL top-k on every rank.  No
  * cross-GPU barrier and no merge launch; alternate two buffers between consecutive searches.  Every rank must make the
- * matching call (a peer that never arrives traps the kernel after 4 s instead of hanging). */
+ * matching call (a peer that never arrives traps the kernel after 60 s instead of hanging). */
 int cir_search_topk_exchange_merge(const void* q, int Q, const void* db, int64_t N, int Kd, int k, int32_t idx_offset,
                                    void* const* peer_bufs, int n_peers, int my_rank, uint32_t arrivals,
                                    float* out_scores, int32_t* out_idx,
