@@ -624,6 +624,10 @@ extern "C" int cir_search_topk_exchange_merge(const void* q, int Q, const void* 
                 CIR_ERR_INVALID_ARG, "cir_search_topk_exchange_merge: bad peer arguments");
     for (int g = 0; g < n_peers; ++g)
         CIR_REQUIRE(peer_bufs[g], CIR_ERR_INVALID_ARG, "cir_search_topk_exchange_merge: null peer buffer");
+    // every selection block waits for its peers: all Q blocks must be resident at once.  Checked before anything is launched.
+    CIR_REQUIRE(Q <= device_info().num_sms && (long long)n_peers * k <= 8192, CIR_ERR_UNSUPPORTED,
+                "cir_search_topk_exchange_merge: the fused merge needs Q <= %d queries and n_peers * k <= 8192 (Q=%d n_peers=%d k=%d)",
+                device_info().num_sms, Q, n_peers, k);
     return search_topk_impl(q, Q, db, N, Kd, k, nullptr, nullptr, nullptr, out_scores, out_idx, idx_offset, workspace,
                             workspace_bytes, flags, stream, peer_bufs, n_peers, my_rank, arrivals);
 }

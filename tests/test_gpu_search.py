@@ -169,6 +169,66 @@ def test_merge_equals_global_topk():
     assert torch.equal(mi2, i_ref) and torch.equal(ms2, s_ref)
 
 
+def test_fused_exchange_merge_two_ranks_on_one_gpu():
+    """cir_search_topk_exchange_merge without a second GPU: two "ranks" (two shards, two streams, two exchange buffers in the
+    same device memory) run concurrently; each selection block stores its list into both buffers, signals both arrival
+    counters, waits for its own and merges.  The result on both ranks == the search over the whole database.  Then the
+    degenerate world of one rank.  (The real thing over NVLink: tests/test_multi_gpu.py, bench.py's parity object.)"""
+    import ctypes as C
+    from cirtorch_b200 import _lib, search as S
+    lib = _lib.load()
+    db, _ = clustered_unit_rows(20_000, 256, 60, 0.7, seed=11)
+    q, _ = clustered_unit_rows(70, 256, 60, 0.7, seed=12)
+    Q, k, G = 70, 50, 2
+    qp = S.pack_rows(_dev(q), "query", "bf16")
+    dbp = S.pack_rows(_dev(db), "db", "bf16")
+    s_ref, i_ref = S.search_packed(qp, dbp, k)
+    bounds = [0, 9_000, 20_000]
+    words = G * 2 * Q * k
+    bufs = [torch.zeros(words + Q, dtype=torch.int32, device=DEV) for _ in range(G)]          # lists + arrival counters
+    peers = (C.c_void_p * G)(*[b.data_ptr() for b in bufs])
+    shards = [dbp[a:b].contiguous() for a, b in zip(bounds[:-1], bounds[1:])]
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    outs = [(torch.empty((Q, k), dtype=torch.float32, device=DEV), torch.empty((Q, k), dtype=torch.int32, device=DEV)) for _ in range(G)]
+    wss = []
+    for r in range(G):
+        need = C.c_size_t(0)
+        _lib.check(lib.cir_search_workspace_bytes(Q, shards[r].shape[0], qp.shape[1], k, C.byref(need)), "ws")
+        wss.append(torch.empty(need.value, dtype=torch.uint8, device=DEV))
+    torch.cuda.synchronize()
+    for use in (1, 2, 3):                       # the counters only grow: the target of use u is u * G
+        for r in range(G):
+            outs[r][1].fill_(-7)
+        torch.cuda.synchronize()
+        for r in range(G):
+            with torch.cuda.stream(streams[r]):
+                rc = lib.cir_search_topk_exchange_merge(_lib.ptr(qp), Q, _lib.ptr(shards[r]), shards[r].shape[0], qp.shape[1], k,
+                                                        bounds[r], peers, G, r, use * G, _lib.ptr(outs[r][0]), _lib.ptr(outs[r][1]),
+                                                        _lib.ptr(wss[r]), wss[r].numel(), 0, streams[r].cuda_stream)
+                _lib.check(rc, "cir_search_topk_exchange_merge")
+        torch.cuda.synchronize()
+        for r in range(G):
+            assert torch.equal(outs[r][1], i_ref) and torch.equal(outs[r][0], s_ref)
+    assert [int(b[words:].min()) for b in bufs] == [3 * G] * G and [int(b[words:].max()) for b in bufs] == [3 * G] * G
+    # one rank: its own buffer is the only peer
+    solo = torch.zeros(2 * Q * k + Q, dtype=torch.int32, device=DEV)
+    need = C.c_size_t(0)
+    _lib.check(lib.cir_search_workspace_bytes(Q, dbp.shape[0], qp.shape[1], k, C.byref(need)), "ws")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=DEV)
+    so, io = torch.empty((Q, k), dtype=torch.float32, device=DEV), torch.empty((Q, k), dtype=torch.int32, device=DEV)
+    rc = lib.cir_search_topk_exchange_merge(_lib.ptr(qp), Q, _lib.ptr(dbp), dbp.shape[0], qp.shape[1], k, 0,
+                                            (C.c_void_p * 1)(solo.data_ptr()), 1, 0, 1, _lib.ptr(so), _lib.ptr(io),
+                                            _lib.ptr(ws), ws.numel(), 0, _lib.stream_of(qp))
+    _lib.check(rc, "cir_search_topk_exchange_merge")
+    assert torch.equal(io, i_ref) and torch.equal(so, s_ref)
+    # more queries than SMs: refused (every block must be resident while it waits), nothing launched that could hang
+    big = S.pack_rows(_dev(np.repeat(q, 3, 0)), "query", "bf16")
+    rc = lib.cir_search_topk_exchange_merge(_lib.ptr(big), 210, _lib.ptr(dbp), dbp.shape[0], qp.shape[1], k, 0,
+                                            (C.c_void_p * 1)(solo.data_ptr()), 1, 0, 2, _lib.ptr(so), _lib.ptr(io),
+                                            _lib.ptr(ws), ws.numel(), 0, _lib.stream_of(qp))
+    assert rc != 0 and b"fused merge" in lib.cir_last_error()
+
+
 def test_many_splits_small_k_large_n():
     """More database tiles than SMs x a few: exercises multi-tile units, list compaction and the select rounds."""
     from cirtorch_b200 import search as S
