@@ -30,6 +30,8 @@ SIGNATURES = {
     "cir_tail_workspace_bytes": (_c_int, [_c_int, _c_int, _c_int, _szp]),
     "cir_tail_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _c_f, _c_int,
                               _vp, _vp, _c_int, _vp, _c_int, _vp, _vp, C.c_size_t, C.c_uint, _vp]),
+    "cir_tail_fwd_train": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _c_f, _c_int,
+                                    _vp, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, C.c_size_t, C.c_uint, _vp]),
     "cir_gem_bwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp]),
     "cir_bias_l2n_rows": (_c_int, [_vp, _c_i64, _c_int, _c_i64, _vp, _c_f, _vp, _c_i64, _vp]),
     "cir_powerlaw": (_c_int, [_vp, _c_i64, _c_f, _vp, _vp]),

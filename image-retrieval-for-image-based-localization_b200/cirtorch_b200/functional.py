@@ -4,6 +4,8 @@ All functions take CUDA fp32 tensors and launch libcir_b200 kernels on the curre
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -22,9 +24,10 @@ def _as_f32_contig(x: torch.Tensor) -> torch.Tensor:
 _tail_ws_bytes = {}
 
 
-def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None, pooled_out=None):
+def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None, pooled_out=None, z_out=None):
     """One cooperative launch of the fused tail.  Returns the physical [N, D] buffer.
-    ``pooled_out``: optional contiguous fp32 [N, C] buffer that receives the pooled values (kept for the backward pass).
+    ``pooled_out`` / ``z_out``: optional contiguous fp32 [N, C] / [N, D] buffers that receive the pooled values and the
+    projection before the last L2N (both kept for the backward pass; cir_tail_fwd_train).
 
     Kept lean on the host (a launch is ~0.1 ms of GPU time): no detach / reshape copies, one stream query."""
     _lib.require_cuda(x, p, weight, bias)
@@ -66,11 +69,19 @@ def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=Non
         _lib.check(lib.cir_tail_workspace_bytes(N, Cc, D, C.byref(c_need)), "cir_tail_workspace_bytes")
         need = _tail_ws_bytes[key] = c_need.value
     ws = _lib.workspace(x.device, need, "tail")
-    rc = lib.cir_tail_fwd(x.data_ptr(), N, Cc, H, W, p.data_ptr() if p is not None else None, p_stride, eps, l2_eps,
-                          pool_mode, weight.data_ptr() if whiten else None,
-                          bias.data_ptr() if (whiten and bias is not None) else None, D,
-                          out.data_ptr(), D, pooled_out.data_ptr() if pooled_out is not None else None,
-                          ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream(x.device).cuda_stream)
+    if z_out is not None:
+        rc = lib.cir_tail_fwd_train(x.data_ptr(), N, Cc, H, W, p.data_ptr() if p is not None else None, p_stride, eps, l2_eps,
+                                    pool_mode, weight.data_ptr() if whiten else None,
+                                    bias.data_ptr() if (whiten and bias is not None) else None, D,
+                                    out.data_ptr(), D, pooled_out.data_ptr() if pooled_out is not None else None,
+                                    z_out.data_ptr(), ws.data_ptr(), ws.numel(), flags,
+                                    torch.cuda.current_stream(x.device).cuda_stream)
+    else:
+        rc = lib.cir_tail_fwd(x.data_ptr(), N, Cc, H, W, p.data_ptr() if p is not None else None, p_stride, eps, l2_eps,
+                              pool_mode, weight.data_ptr() if whiten else None,
+                              bias.data_ptr() if (whiten and bias is not None) else None, D,
+                              out.data_ptr(), D, pooled_out.data_ptr() if pooled_out is not None else None,
+                              ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream(x.device).cuda_stream)
     if rc:
         _lib.check(rc, "cir_tail_fwd")
     return out
@@ -126,6 +137,9 @@ def _colsum_rows(x2d):
     return out
 
 
+_NO_ZOUT = bool(int(os.environ.get("CIR_DEBUG_NO_ZOUT", "0")))      # experiments: recompute the projection in backward
+
+
 class _TailFn(torch.autograd.Function):
     """Forward = the fused CUDA kernel (which also hands back the pooled values g).  Backward for GeM pooling: two
     row kernels for the L2N gradients (cir_l2n_bwd_rows), the three [N, C] x [C, D]-sized products of the Linear through
@@ -137,19 +151,23 @@ class _TailFn(torch.autograd.Function):
     def forward(ctx, x, p, weight, bias, eps, pooling, flags, l2_eps):
         ctx.cfg = (eps, pooling, flags, l2_eps)
         xc = _as_f32_contig(x)
-        g = None
+        g = z = None
         gem_path = pooling in ("GeM", "GeMmp") and xc.shape[0] > 0
         if gem_path and not (flags & CIR_TAIL_POOL_ONLY):
             g = torch.empty((xc.shape[0], xc.shape[1]), dtype=torch.float32, device=xc.device)
-        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, pooled_out=g)
+            if not (flags & CIR_TAIL_NO_WHITEN) and not _NO_ZOUT:
+                # the projection before the last L2N, stored by the kernel's last phase: the backward would otherwise recompute
+                # it with a 64 x 2048 x 2048 fp32 GEMM (51 us of the 0.49 ms forward + backward)
+                z = torch.empty((xc.shape[0], weight.shape[0]), dtype=torch.float32, device=xc.device)
+        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, pooled_out=g, z_out=z)
         if gem_path and (flags & CIR_TAIL_POOL_ONLY):
             g = out
-        ctx.save_for_backward(xc, p, weight, bias, g)
+        ctx.save_for_backward(xc, p, weight, bias, g, z)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, p, weight, bias, g = ctx.saved_tensors
+        x, p, weight, bias, g, z = ctx.saved_tensors
         eps, pooling, flags, l2_eps = ctx.cfg
         need = ctx.needs_input_grad
         if g is None:
@@ -163,7 +181,8 @@ class _TailFn(torch.autograd.Function):
                 dg, _ = _l2n_bwd_rows(g, gout, l2_eps)
             else:
                 _, u = _l2n_bwd_rows(g, None, l2_eps, want_unit=True)          # u = g / (||g|| + eps)
-                z = torch.addmm(bias, u, weight.t()) if bias is not None else u @ weight.t()
+                if z is None:
+                    z = torch.addmm(bias, u, weight.t()) if bias is not None else u @ weight.t()
                 dz, _ = _l2n_bwd_rows(z, gout, l2_eps)
                 if need[2]:
                     dW = dz.t() @ u
@@ -187,7 +206,7 @@ class _TailFn(torch.autograd.Function):
 
     @staticmethod
     def _backward_recompute(ctx, g):
-        x, p, weight, bias, _ = ctx.saved_tensors
+        x, p, weight, bias, _, _ = ctx.saved_tensors
         eps, pooling, flags, l2_eps = ctx.cfg
         ins = []
         with torch.enable_grad():

@@ -61,7 +61,7 @@ extern "C" {
 
 const char* cir_last_error(void) { return cir::g_err; }
 
-int cir_version(void) { return 200; }   // 200: round 2 (cir_tail_fwd gained pooled_out; training, radix-sort and loss entry points)
+int cir_version(void) { return 210; }   // 200: round 2 (pooled_out; training, radix-sort and loss entry points); 210: + cir_tail_fwd_train, cir_search_topk_exchange_merge
 
 int64_t cir_launch_count(int reset) {
     int64_t v = cir::g_launches;

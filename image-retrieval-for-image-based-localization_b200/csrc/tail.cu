@@ -68,6 +68,7 @@ struct TailParams {
     __nv_bfloat16* pooled_hi;   // whiten mode: pooled vectors as bf16 hi + lo parts, [N, C] each (same bytes as fp32)
     __nv_bfloat16* pooled_lo;
     float* pooled_out; // optional caller-owned [N, C] fp32 copy of the pooled values (kept for the backward pass)
+    float* z_out;      // optional caller-owned [N, D_out] fp32: the projection W.L2N(g) + b BEFORE the last L2N (backward pass)
     float* part;       // [n_kslices][N][D_out] partial projections of the K slices
     int n_ntiles, n_kslices, units;   // projection units: u = ks * n_ntiles + nt
     unsigned flags;
@@ -744,6 +745,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                 if (d < P.D_out) {
                     yreg[i] = yreg[i] * inv + breg[i];
                     sy = fmaf(yreg[i], yreg[i], sy);
+                    if (P.z_out) P.z_out[(size_t)n * P.D_out + d] = yreg[i];
                 }
             }
             for (int d = tid + YR * TAIL_THREADS; d < P.D_out; d += TAIL_THREADS) {
@@ -751,6 +753,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                 for (int ks = 0; ks < P.n_kslices; ++ks) acc += __ldcg(P.part + ((size_t)ks * P.N + n) * P.D_out + d);
                 const float y = acc * inv + (P.bias ? __ldg(P.bias + d) : 0.0f);
                 sy = fmaf(y, y, sy);
+                if (P.z_out) P.z_out[(size_t)n * P.D_out + d] = y;
             }
             const float denom = sqrtf(block_sum(sy, 1)) + P.eps_l2;
 #pragma unroll
@@ -805,10 +808,33 @@ extern "C" int cir_tail_workspace_bytes(int N, int C, int D_out, size_t* bytes) 
     return CIR_OK;
 }
 
+static int tail_fwd_impl(const float* x, int N, int C, int H, int W, const float* p, int p_stride,
+                         float eps_gem, float eps_l2, int pool_mode, const float* Wt,
+                         const float* bias, int D_out, float* out, int out_ld, float* pooled_out, float* z_out, void* workspace,
+                         size_t workspace_bytes, unsigned flags, void* stream);
+
 extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const float* p, int p_stride,
                             float eps_gem, float eps_l2, int pool_mode, const float* Wt,
                             const float* bias, int D_out, float* out, int out_ld, float* pooled_out, void* workspace,
                             size_t workspace_bytes, unsigned flags, void* stream) {
+    return tail_fwd_impl(x, N, C, H, W, p, p_stride, eps_gem, eps_l2, pool_mode, Wt, bias, D_out, out, out_ld, pooled_out, nullptr,
+                         workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int cir_tail_fwd_train(const float* x, int N, int C, int H, int W, const float* p, int p_stride,
+                                  float eps_gem, float eps_l2, int pool_mode, const float* Wt,
+                                  const float* bias, int D_out, float* out, int out_ld, float* pooled_out, float* z_out,
+                                  void* workspace, size_t workspace_bytes, unsigned flags, void* stream) {
+    CIR_REQUIRE(!z_out || !(flags & (CIR_TAIL_POOL_ONLY | CIR_TAIL_NO_WHITEN)), CIR_ERR_INVALID_ARG,
+                "cir_tail_fwd_train: z_out is the whitening projection; not available with CIR_TAIL_POOL_ONLY / CIR_TAIL_NO_WHITEN");
+    return tail_fwd_impl(x, N, C, H, W, p, p_stride, eps_gem, eps_l2, pool_mode, Wt, bias, D_out, out, out_ld, pooled_out, z_out,
+                         workspace, workspace_bytes, flags, stream);
+}
+
+static int tail_fwd_impl(const float* x, int N, int C, int H, int W, const float* p, int p_stride,
+                         float eps_gem, float eps_l2, int pool_mode, const float* Wt,
+                         const float* bias, int D_out, float* out, int out_ld, float* pooled_out, float* z_out, void* workspace,
+                         size_t workspace_bytes, unsigned flags, void* stream) {
     CIR_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0, CIR_ERR_INVALID_ARG,
                 "cir_tail_fwd: null pointer or empty shape (N=%d C=%d H=%d W=%d)", N, C, H, W);
     CIR_REQUIRE(pool_mode >= CIR_POOL_GEM && pool_mode <= CIR_POOL_SPOC, CIR_ERR_INVALID_ARG,
@@ -829,6 +855,7 @@ extern "C" int cir_tail_fwd(const float* x, int N, int C, int H, int W, const fl
     P.p = p; P.p_stride = p_stride; P.eps_gem = eps_gem; P.eps_l2 = eps_l2; P.pool_mode = pool_mode;
     P.Wt = Wt; P.bias = bias; P.D_out = D_out; P.out = out; P.out_ld = out_ld; P.flags = flags;
     P.pooled_out = pool_only ? nullptr : pooled_out;
+    P.z_out = z_out;
     P.vec_ok = ((P.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     P.bulk_ok = P.vec_ok && (size_t)P.HW * 4 <= (size_t)TAIL_SLOT_BYTES;
     {

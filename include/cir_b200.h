@@ -54,7 +54,7 @@ extern "C" {
 #define CIR_SEARCH_SAMPLE_FIRST_ROWS 2u /* threshold sample = the first rows instead of 32-row pieces spread over the matrix */
 
 const char* cir_last_error(void);
-int cir_version(void);            /* 100 = round 1, 200 = round 2 (cir_tail_fwd gained pooled_out; section 7 added) */
+int cir_version(void);            /* 100 = round 1, 200 = round 2 (cir_tail_fwd gained pooled_out; section 7 added), 210 = cir_tail_fwd_train, cir_search_topk_exchange_merge */
 /* number of kernels launched by this library on the calling thread since the last reset
  * (bench.py's gpu_launches counter) */
 int64_t cir_launch_count(int reset);
@@ -84,6 +84,15 @@ int cir_tail_fwd(const float* x, int N, int C, int H, int W,
                  const float* Wt, const float* bias, int D_out,
                  float* out, int out_ld, float* pooled_out,
                  void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
+/* The same launch for the training forward: additionally stores z = W . L2N(pool(x)) + b, the projection BEFORE the last L2N,
+ * into z_out [N, D_out] fp32 (NULL = not wanted) -- the backward of the final L2N and of the Linear need it, and
+ * recomputing it is a 64 x 2048 x 2048 fp32 GEMM. */
+int cir_tail_fwd_train(const float* x, int N, int C, int H, int W,
+                       const float* p, int p_stride, float eps_gem, float eps_l2, int pool_mode,
+                       const float* Wt, const float* bias, int D_out,
+                       float* out, int out_ld, float* pooled_out, float* z_out,
+                       void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 
 /* Backward of the GeM pooling over the feature map (training, scripts/train_globalF.py:480-488; the autograd of
  * pools.py:37-38): dx[n,c,:,:] = dg[n,c] * g[n,c]^(1-p) * max(x,eps)^(p-1) / (H W) where x >= eps, and, when S != NULL,

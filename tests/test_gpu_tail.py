@@ -305,6 +305,36 @@ def test_gradients_all_modes(pooling, p, mode):
         assert err < 2e-3, (k, err)
 
 
+def test_training_forward_saves_projection():
+    """cir_tail_fwd_train: the descriptors are those of cir_tail_fwd (bit-equal), pooled_out = the GeM values and z_out = the
+    projection before the last L2N (global_head.py:62-64), so that out == L2N(z_out)."""
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(9)
+    x = (torch.relu(torch.randn(7, 256, 12, 16)) + 0.01).to(DEV)
+    head = _head(256, "GeM", p=2.6).to(DEV)
+    W, b, pt = head.whiten.weight.detach(), head.whiten.bias.detach(), head.pool.p.detach()
+    g = torch.empty((7, 256), device=DEV)
+    z = torch.empty((7, 256), device=DEV)
+    out_t = LF._tail_launch(x, pt, 1e-6, W, b, LF._POOL["GeM"], 0, pooled_out=g, z_out=z)
+    out = LF._tail_launch(x, pt, 1e-6, W, b, LF._POOL["GeM"], 0)
+    assert torch.equal(out, out_t)
+    g_ref = O.gem(x.cpu(), pt.cpu()).flatten(1)
+    u = g_ref / (g_ref.norm(dim=1, keepdim=True) + 1e-6)
+    z_ref = u.double() @ W.cpu().double().t() + b.cpu().double()
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref.numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(z.cpu().numpy(), z_ref.numpy(), rtol=0, atol=2e-5)
+    zn = z / (z.norm(dim=1, keepdim=True) + 1e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), zn.cpu().numpy(), rtol=0, atol=1e-6)
+    # z_out is the whitening projection: refused where there is none
+    import ctypes as C
+    from cirtorch_b200 import _lib
+    lib = _lib.load()
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    rc = lib.cir_tail_fwd_train(x.data_ptr(), 7, 256, 12, 16, pt.data_ptr(), 0, 1e-6, 1e-6, 0, None, None, 256, out.data_ptr(), 256,
+                                None, z.data_ptr(), ws.data_ptr(), ws.numel(), LF.CIR_TAIL_NO_WHITEN, None)
+    assert rc != 0 and b"z_out" in lib.cir_last_error()
+
+
 def test_cpu_tensor_is_rejected():
     from cirtorch_b200._lib import CirError
     head = _head(16)

@@ -180,6 +180,10 @@ def test_entry_points_validate_before_touching_the_device():
     assert lib.cir_tail_workspace_bytes(64, 2048, 2048, C.byref(need)) == 0 and need.value > 64 * 2048 * 4
     calls = {
         "cir_tail_fwd": lambda: lib.cir_tail_fwd(None, 1, 8, 4, 4, None, 0, 1e-6, 1e-6, 0, None, None, 8, None, 8, None, None, 0, 0, None),
+        "cir_tail_fwd_train": lambda: lib.cir_tail_fwd_train(None, 1, 8, 4, 4, None, 0, 1e-6, 1e-6, 0, None, None, 8, None, 8, None,
+                                                             C.c_void_p(256), None, 0, _lib.CIR_TAIL_NO_WHITEN, None),
+        "cir_search_topk_exchange_merge": lambda: lib.cir_search_topk_exchange_merge(None, 70, None, 10, 64, 5, 0, None, 1, 0, 1, None,
+                                                                                     None, None, 0, 0, None),
         "cir_gem_bwd": lambda: lib.cir_gem_bwd(None, 1, 8, 4, 4, None, 0, 1e-6, None, None, None, None, None),
         "cir_region_pool": lambda: lib.cir_region_pool(None, 1, 8, 4, 4, None, 1, None, 0, 1e-6, 0, None, None),
         "cir_l2n_rows": lambda: lib.cir_l2n_rows(None, 1, 8, 8, 1e-6, None, 8, None),
