@@ -7,7 +7,8 @@
 //   radix_hist_kernel     256-bin histogram of every 4096-key chunk               (4 B read per key)
 //   radix_scan_kernel     per row, exclusive prefix over (digit, chunk)           (tiny)
 //   radix_scatter_kernel  re-reads the chunk in the same order, ranks every key inside its digit with warp MATCH.ANY
-//                         votes (no atomics, deterministic) and writes key + index to their final place of the pass
+//                         votes (no atomics, deterministic), orders the chunk by digit in shared memory and writes every
+//                         digit's run of keys + indices contiguously to its place of the pass
 //                                                                                 (8 B read + 8 B written per key)
 // Pass 0 builds keys from the fp32 scores on the fly, pass 3 writes the int32 ranks (and optionally the sorted scores)
 // straight to the outputs.  Algorithmic traffic: 4 x 20 B per element (70 x 1M: 5.6 GB); HBM-bound, scattered writes.
@@ -99,6 +100,10 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(int* __restrict__ hist
 
 __global__ void __launch_bounds__(RDX_THREADS) radix_scatter_kernel(const RadixArgs a) {
     __shared__ int cnt[RDX_WARPS][256];
+    __shared__ int gbase[256];              // where the chunk's keys of digit d start in the row (this pass's output)
+    __shared__ int lbase[256 + 1];          // where they start inside the chunk once it is ordered by digit
+    __shared__ uint32_t skey[RDX_CHUNK];    // the chunk ordered by digit: a digit's keys leave as ONE contiguous run
+    __shared__ int32_t sval[RDX_CHUNK];
     const int q = blockIdx.y, blk = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int t = threadIdx.x; t < RDX_WARPS * 256; t += RDX_THREADS) (&cnt[0][0])[t] = 0;
@@ -124,18 +129,36 @@ __global__ void __launch_bounds__(RDX_THREADS) radix_scatter_kernel(const RadixA
         __syncwarp();
     }
     __syncthreads();
-    {   // digit d: positions of the chunk's keys of that digit start at hist[q][d][blk]; warps in order behind it
+    int tot = 0;
+    {   // digit d = threadIdx.x: the warps' counts become their start inside the digit's run; tot = keys of the digit in the chunk
         const int d = threadIdx.x;
-        int run = a.hist[((size_t)q * 256 + d) * a.nblk + blk];
+        gbase[d] = a.hist[((size_t)q * 256 + d) * a.nblk + blk];
 #pragma unroll
         for (int w = 0; w < RDX_WARPS; ++w) {
             const int c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
+            cnt[w][d] = tot;
+            tot += c;
         }
     }
+    {   // exclusive prefix of the digit totals over the 256 threads -> lbase
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        __shared__ int wsum[RDX_WARPS];
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < RDX_WARPS; ++w) before += w < warp ? wsum[w] : 0;
+        lbase[threadIdx.x] = before + inc - tot;
+        if (threadIdx.x == RDX_THREADS - 1) lbase[256] = before + inc;
+    }
     __syncthreads();
-    const size_t row = (size_t)q * a.N;
+    // The scatter used to write every key straight to its place: the 32 lanes of a store hit ~27 different digit runs, i.e. 27
+    // sectors for 128 bytes.  Ordered by digit in shared memory first, consecutive threads write consecutive places of a run.
 #pragma unroll
     for (int t = 0; t < RDX_PER_LANE; ++t) {
         const bool valid = val[t] >= 0;
@@ -143,18 +166,28 @@ __global__ void __launch_bounds__(RDX_THREADS) radix_scatter_kernel(const RadixA
         if (valid) {
             const uint32_t d = (key[t] >> shift) & 255u;
             const unsigned peers = __match_any_sync(vmask, d);
-            const int pos = cnt[warp][d] + __popc(peers & lt);
+            const int l = lbase[d] + cnt[warp][d] + __popc(peers & lt);
             __syncwarp(vmask);
             if ((peers & lt) == 0) cnt[warp][d] += __popc(peers);
-            if (a.pass == 3) {
-                a.final_idx[row + pos] = val[t];
-                if (a.final_sorted) a.final_sorted[row + pos] = radix_to_score(key[t]);
-            } else {
-                a.out_keys[row + pos] = key[t];
-                a.out_vals[row + pos] = val[t];
-            }
+            skey[l] = key[t];
+            sval[l] = val[t];
         }
         __syncwarp();
+    }
+    __syncthreads();
+    const size_t row = (size_t)q * a.N;
+    const int n_chunk = lbase[256];
+    for (int l = threadIdx.x; l < n_chunk; l += RDX_THREADS) {
+        const uint32_t k = skey[l];
+        const uint32_t d = (k >> shift) & 255u;
+        const size_t pos = row + (size_t)(gbase[d] + (l - lbase[d]));
+        if (a.pass == 3) {
+            a.final_idx[pos] = sval[l];
+            if (a.final_sorted) a.final_sorted[pos] = radix_to_score(k);
+        } else {
+            a.out_keys[pos] = k;
+            a.out_vals[pos] = sval[l];
+        }
     }
 }
 
