@@ -335,6 +335,26 @@ def test_training_forward_saves_projection():
     assert rc != 0 and b"z_out" in lib.cir_last_error()
 
 
+@pytest.mark.parametrize("p", [3.0, 2.7])
+def test_launches_are_bit_identical(p):
+    """Ring hand-over races (a slot refilled while a row is still being read) show up as launches that differ: 40 launches of
+    the full-size batch, other data through the ring in between, pool-only and full -- all bit-identical to the first."""
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(21)
+    x = torch.relu(torch.randn(64, 2048, 32, 32, device=DEV))
+    other = torch.relu(torch.randn(64, 2048, 32, 32, device=DEV))
+    head = _head(2048, p=p).to(DEV)
+    pt = torch.full((1,), p, device=DEV)
+    with torch.no_grad():
+        ref = head(x).clone()
+        ref_pool = LF.descriptor_tail(x, p=pt, pooling="GeM", pool_only=True).clone()
+        for i in range(40):
+            if i % 3 == 0:
+                head(other)
+            assert torch.equal(head(x), ref), i
+            assert torch.equal(LF.descriptor_tail(x, p=pt, pooling="GeM", pool_only=True), ref_pool), i
+
+
 def test_cpu_tensor_is_rejected():
     from cirtorch_b200._lib import CirError
     head = _head(16)
