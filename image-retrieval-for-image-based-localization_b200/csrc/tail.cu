@@ -190,6 +190,40 @@ __device__ __forceinline__ float row_partial_vec(const float4* v, int nvec, int 
     for (; i < nvec; i += 32) a0 = fold4<PM>(a0, GLOBAL ? ld_stream_f4(v + i) : lds_f4(sa + (uint32_t)i * 16u), eps, p);
     return PM == PM_MAX ? fmaxf(a0, a1) : a0 + a1;
 }
+// The same for a row in a ring slot, handing the slot back as soon as the row sits in REGISTERS: with a non-integer exponent
+// the folding is most of a row's time, and the producer can refill the slot that much earlier.  The arrival must not be issued
+// while a load is in flight -- the refilling bulk copy (async proxy) overtakes it (measured: launches differed) -- so one
+// component of each of the eight vectors is clamped first (the fold clamps it anyway): those FMNMX cannot issue before the
+// loads have returned, and the arrival is issued after them.
+// Returns true if the slot was released here (rows whose vector count is not a multiple of 256 are released by the caller).
+template <int PM>
+__device__ __forceinline__ bool row_partial_vec_release(const float4* v, int nvec, int lane, float eps, float p, uint64_t* empty_bar,
+                                                        float* out) {
+    float a0 = 0.0f, a1 = 0.0f;
+    const uint32_t sa = smem_u32(v);
+    const bool whole = (nvec & 255) == 0;
+    int i = lane;
+    for (; i + 32 * 7 < nvec; i += 256) {
+        float4 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = lds_f4(sa + (uint32_t)(i + 32 * j) * 16u);
+        if (whole && i + 256 >= nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j].x = fmaxf(u[j].x, eps);
+            asm volatile("" : "+f"(u[0].x), "+f"(u[1].x), "+f"(u[2].x), "+f"(u[3].x), "+f"(u[4].x), "+f"(u[5].x), "+f"(u[6].x), "+f"(u[7].x));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            a0 = fold4<PM>(a0, u[j], eps, p);
+            a1 = fold4<PM>(a1, u[j + 1], eps, p);
+        }
+    }
+    for (; i < nvec; i += 32) a0 = fold4<PM>(a0, lds_f4(sa + (uint32_t)i * 16u), eps, p);
+    *out = a0 + a1;
+    return whole && nvec > 0;
+}
 template <int PM>
 __device__ __forceinline__ float row_partial_scalar(const float* x, int n, int lane, float eps, float p) {
     float a = PM == PM_MAX ? -INFINITY : 0.0f;
@@ -471,15 +505,22 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constan
                         mbar_wait(&full_bar[bar], par);
                         const float* src = reinterpret_cast<const float*>(ring + (size_t)slot * TAIL_SLOT_BYTES) + (size_t)j * HW;
                         float a;
-                        if constexpr (PMC >= 0) {
+                        bool released = false;
+                        if constexpr (PMC == PM_GENERAL || PMC >= PM_GENERAL_POLY0) {
+                            released = row_partial_vec_release<PMC>(reinterpret_cast<const float4*>(src), HW >> 2, lane, P.eps_gem, p_shared,
+                                                                    &empty_bar[bar], &a);
+                            a = warp_sum(a);
+                        } else if constexpr (PMC >= 0) {
                             a = row_partial_vec<PMC, false>(reinterpret_cast<const float4*>(src), HW >> 2, lane, P.eps_gem, p_shared);
                             a = PMC == PM_MAX ? warp_max(a) : warp_sum(a);
                         } else {
                             const float pr = __ldg(P.p + cur_c);
                             a = row_reduce<false>(classify_p(P.pool_mode, pr, P.gen_mode), src, HW, true, lane, P.eps_gem, pr);
                         }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[bar]);        // one arrival per row: count = rows per slot
+                        if (!released) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty_bar[bar]);    // one arrival per row: count = rows per slot
+                        }
                         take(a, cur_n, cur_c);
                         next_row();
                         j += step_r;                            // advance to the slot iteration holding row i + NC
