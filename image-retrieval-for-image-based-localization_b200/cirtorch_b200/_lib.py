@@ -65,7 +65,7 @@ SIGNATURES = {
 }
 
 CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC = 0, 1, 2
-CIR_TAIL_NO_WHITEN, CIR_TAIL_POOL_ONLY, CIR_TAIL_ACCUMULATE = 1, 2, 4
+CIR_TAIL_NO_WHITEN, CIR_TAIL_POOL_ONLY, CIR_TAIL_ACCUMULATE, CIR_TAIL_HINT_INTEGER_P = 1, 2, 4, 8
 
 _lib = None
 _lock = threading.Lock()

@@ -9,7 +9,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC, CIR_TAIL_ACCUMULATE, CIR_TAIL_NO_WHITEN,
+from ._lib import (CIR_POOL_GEM, CIR_POOL_MAC, CIR_POOL_SPOC, CIR_TAIL_ACCUMULATE, CIR_TAIL_HINT_INTEGER_P, CIR_TAIL_NO_WHITEN,
                    CIR_TAIL_POOL_ONLY)
 
 _POOL = {"GeM": CIR_POOL_GEM, "GeMmp": CIR_POOL_GEM, "MAC": CIR_POOL_MAC, "SPoC": CIR_POOL_SPOC}
@@ -24,7 +24,21 @@ def _as_f32_contig(x: torch.Tensor) -> torch.Tensor:
 _tail_ws_bytes = {}
 
 
-def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None, pooled_out=None, z_out=None):
+def _integer_p_hint(p) -> int:
+    """CIR_TAIL_HINT_INTEGER_P if the (single, frozen) GeM exponent is a small integer.  The exponent lives on the device; it is
+    read back ONCE per tensor object and version -- an inference-time constant -- and only picks the launch shape, never the
+    result.  The answer is kept on the tensor itself (a dictionary keyed by address would outlive the tensor)."""
+    hit = getattr(p, "_cir_integer_p", None)
+    if hit is None or hit[0] != p._version:
+        hit = (p._version, float(p.detach().reshape(-1)[0]) in (1.0, 2.0, 3.0, 4.0))
+        try:
+            p._cir_integer_p = hit
+        except AttributeError:        # a tensor type that takes no attributes: read back every time rather than guess
+            pass
+    return CIR_TAIL_HINT_INTEGER_P if hit[1] else 0
+
+
+def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=None, pooled_out=None, z_out=None, allow_hint=True):
     """One cooperative launch of the fused tail.  Returns the physical [N, D] buffer.
     ``pooled_out`` / ``z_out``: optional contiguous fp32 [N, C] / [N, D] buffers that receive the pooled values and the
     projection before the last L2N (both kept for the backward pass; cir_tail_fwd_train).
@@ -50,6 +64,8 @@ def _tail_launch(x, p, eps, weight, bias, pool_mode, flags, l2_eps=1e-6, out=Non
     if p is not None:
         if p.dtype != torch.float32 or not p.is_contiguous():
             p = p.detach().float().contiguous()
+        elif allow_hint and p.numel() == 1 and not (p.requires_grad and torch.is_grad_enabled()):
+            flags |= _integer_p_hint(p)
         np_ = p.numel()
         if np_ not in (1, Cc):
             raise ValueError("GeM exponent must have 1 or C=%d elements, got %d" % (Cc, np_))
@@ -159,7 +175,8 @@ class _TailFn(torch.autograd.Function):
                 # the projection before the last L2N, stored by the kernel's last phase: the backward would otherwise recompute
                 # it with a 64 x 2048 x 2048 fp32 GEMM (51 us of the 0.49 ms forward + backward)
                 z = torch.empty((xc.shape[0], weight.shape[0]), dtype=torch.float32, device=xc.device)
-        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, pooled_out=g, z_out=z)
+        # training: the exponent moves with every optimiser step -- no read-back, the general launch shape
+        out = _tail_launch(xc, p, eps, weight, bias, _POOL[pooling], flags, l2_eps, pooled_out=g, z_out=z, allow_hint=False)
         if gem_path and (flags & CIR_TAIL_POOL_ONLY):
             g = out
         ctx.save_for_backward(xc, p, weight, bias, g, z)
@@ -246,7 +263,9 @@ def descriptor_tail(x, p=None, eps=1e-6, weight=None, bias=None, pooling="GeM", 
         if p is None:
             raise ValueError("GeM pooling needs the exponent p")
         if not torch.is_tensor(p):
-            p = torch.full((1,), float(p), dtype=torch.float32, device=x.device)
+            pf = float(p)
+            p = torch.full((1,), pf, dtype=torch.float32, device=x.device)
+            p._cir_integer_p = (p._version, pf in (1.0, 2.0, 3.0, 4.0))                 # known on the host: no read-back
     else:
         p = None
     needs_grad = torch.is_grad_enabled() and any(

@@ -37,9 +37,15 @@ namespace cir {
 
 using namespace ptx;
 
-constexpr int TAIL_THREADS = 512;
-constexpr int TAIL_WARPS = TAIL_THREADS / 32;
-constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: warps 0..14 consume, warp 15 produces
+// Two launch shapes of the same kernel.  512 threads (15 consumer warps + 1 producer, 120 registers): the integer exponents,
+// MAC and SPoC -- a row is a handful of FMAs per element.  640 threads (19 + 1, 96 registers): everything else.  With a
+// non-integer exponent a row is two MUFU operations per element, the dependent chain of a row is long and 3.75 warps per
+// scheduler leave the MUFU pipe idle between rows; a fifth warp per scheduler is worth 4-5 us per launch (64 x 2048 x 32 x 32,
+// p = 2.7: 102.6 -> 98.1 us), and costs the integer path 0.4 us (94.0 -> 94.5) -- so the host picks, from a hint, and the result
+// never depends on the hint being right (the exponent is classified on the device either way).  576: 104.0 us, 704 / 768
+// threads (80 registers, spills): 99.8 / 97.2 us at p = 2.7 but 95.4-95.7 us at p = 3.
+constexpr int TAIL_THREADS_LIGHT = 512;
+constexpr int TAIL_THREADS_HEAVY = 640;
 constexpr int TAIL_NT = 128;                         // output dims per projection unit (UMMA N)
 constexpr int TAIL_KS = 256;                         // K slice per projection unit (4 k blocks of 64)
 constexpr int TAIL_SLOT_BYTES = 16384;               // one ring slot: whole rows (phase A) / one 128 x 64 bf16 A tile (phase B)
@@ -347,8 +353,11 @@ __device__ __forceinline__ void convert_w_tile(const TailParams& P, unsigned cha
     fence_proxy_async();       // the tiles are read by the tensor core (async proxy)
 }
 
+template <int TAIL_THREADS>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
 tail_fused_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, const TailParams P) {
+    constexpr int TAIL_WARPS = TAIL_THREADS / 32;
+    constexpr int TAIL_CONSUMERS = TAIL_WARPS - 1;       // phase A: all warps but the last consume, the last one produces
     extern __shared__ __align__(1024) unsigned char tail_smem_raw[];
     unsigned char* tail_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* Bt = tail_smem;                                                 // W slice as UMMA B tiles (whiten)
@@ -952,18 +961,26 @@ static int tail_fwd_impl(const float* x, int N, int C, int H, int W, const float
     }
     static thread_local int attr_set_dev = -1;
     if (attr_set_dev != dev.device) {
-        CIR_CHECK_CUDA(cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(tail_fused_kernel<TAIL_THREADS_LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            dev.max_smem_optin - static_smem));
+        CIR_CHECK_CUDA(cudaFuncSetAttribute(tail_fused_kernel<TAIL_THREADS_HEAVY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             dev.max_smem_optin - static_smem));
         attr_set_dev = dev.device;
     }
+    // launch shape (see TAIL_THREADS_*): light rows = MAC / SPoC, or GeM when the caller vouches for an integer exponent
+    static const char* dbg_threads = getenv("CIR_TAIL_THREADS");       // experiments: 512 / 640
+    bool light = pool_mode != CIR_POOL_GEM || (flags & CIR_TAIL_HINT_INTEGER_P);
+    if (dbg_threads) light = atoi(dbg_threads) == TAIL_THREADS_LIGHT;
+    const void* kern = light ? (const void*)tail_fused_kernel<TAIL_THREADS_LIGHT> : (const void*)tail_fused_kernel<TAIL_THREADS_HEAVY>;
+    const int threads = light ? TAIL_THREADS_LIGHT : TAIL_THREADS_HEAVY;
     void* args[] = {&tmHi, &tmLo, &P};
     if (pool_only) {
         // no grid barrier on this path: a plain launch is enough
-        tail_fused_kernel<<<grid, TAIL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmHi, tmLo, P);
+        if (light) tail_fused_kernel<TAIL_THREADS_LIGHT><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(tmHi, tmLo, P);
+        else tail_fused_kernel<TAIL_THREADS_HEAVY><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(tmHi, tmLo, P);
         CIR_CHECK_CUDA(cudaGetLastError());
     } else {
-        CIR_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)tail_fused_kernel, dim3(grid), dim3(TAIL_THREADS),
-                                                   args, smem, static_cast<cudaStream_t>(stream)));
+        CIR_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, static_cast<cudaStream_t>(stream)));
     }
     count_launch();
     return CIR_OK;

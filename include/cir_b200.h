@@ -45,6 +45,10 @@ extern "C" {
 #define CIR_TAIL_POOL_ONLY 2u   /* stop after pooling: GeM.forward alone (no L2N)       */
 #define CIR_TAIL_ACCUMULATE 4u  /* out += descriptor instead of out = descriptor: the sum over scales of the multi-scale
                                    mean, ImageRetrievalNet.forward cirtorch/models/GF_net.py:74-92 (divide by S afterwards) */
+#define CIR_TAIL_HINT_INTEGER_P 8u /* performance hint, never changes the result: the caller knows that the GeM exponent is
+                                    * 1, 2, 3 or 4 (p lives on the device; the library does not read it on the host).  Rows are
+                                    * then cheap and the launch uses 512 threads / 120 registers; without the hint 640 / 96,
+                                    * which suits the two MUFU operations per element of a non-integer exponent */
 #define CIR_TAIL_DEBUG_STAMPS 0x80000000u /* profiling aid: every CTA writes %globaltimer at its phase
                                    boundaries into the last 64 KB of the workspace ([cta][8] u64) */
 

@@ -355,6 +355,35 @@ def test_launches_are_bit_identical(p):
             assert torch.equal(LF.descriptor_tail(x, p=pt, pooling="GeM", pool_only=True), ref_pool), i
 
 
+@pytest.mark.parametrize("p", [3.0, 2.7])
+def test_launch_shape_hint_never_changes_the_result(p):
+    """CIR_TAIL_HINT_INTEGER_P only picks the launch shape (512 threads for cheap rows, 640 for two MUFU operations per
+    element); the exponent is classified on the device either way.  Right hint, wrong hint, no hint: the same descriptors
+    (the row sums are bit-equal; the final norms are summed in a thread-count-dependent order, hence 1e-6) == the oracle."""
+    from cirtorch_b200 import functional as LF
+    torch.manual_seed(13)
+    x = (torch.relu(torch.randn(9, 256, 20, 24)) + 0.01).to(DEV)
+    head = _head(256, "GeM", p=p).to(DEV)
+    W, b, pt = head.whiten.weight.detach(), head.whiten.bias.detach(), head.pool.p.detach()
+    ref = O.head_forward(x.cpu(), pt.cpu(), 1e-6, W.cpu(), b.cpu()).t().numpy()
+    outs = []
+    for flags in (0, LF.CIR_TAIL_HINT_INTEGER_P):
+        o = LF._tail_launch(x, pt, 1e-6, W, b, LF._POOL["GeM"], flags, allow_hint=False)
+        g = LF._tail_launch(x, pt, 1e-6, None, None, LF._POOL["GeM"], flags | LF.CIR_TAIL_POOL_ONLY, allow_hint=False)
+        np.testing.assert_allclose(o.cpu().numpy(), ref, rtol=0, atol=1e-5)
+        outs.append((o, g))
+    assert torch.equal(outs[0][1], outs[1][1])                                # pooled values: bit-equal across launch shapes
+    np.testing.assert_allclose(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy(), rtol=0, atol=1e-6)
+    # the module path picks the hint itself from the frozen exponent (one read-back per tensor version)
+    with torch.no_grad():
+        np.testing.assert_allclose(head(x).t().cpu().numpy(), ref, rtol=0, atol=1e-5)
+    assert head.pool.p._cir_integer_p == (head.pool.p._version, p == 3.0)
+    with torch.no_grad():
+        head.pool.p.fill_(2.5 if p == 3.0 else 4.0)            # a new version of the tensor: read back again
+        head(x)
+    assert head.pool.p._cir_integer_p == (head.pool.p._version, p != 3.0)
+
+
 def test_cpu_tensor_is_rejected():
     from cirtorch_b200._lib import CirError
     head = _head(16)
