@@ -30,6 +30,8 @@ def _integer_p_hint(p) -> int:
     result.  The answer is kept on the tensor itself (a dictionary keyed by address would outlive the tensor)."""
     hit = getattr(p, "_cir_integer_p", None)
     if hit is None or hit[0] != p._version:
+        if torch.cuda.is_current_stream_capturing():
+            return 0                  # no read-back inside a CUDA graph capture: the general launch shape
         hit = (p._version, float(p.detach().reshape(-1)[0]) in (1.0, 2.0, 3.0, 4.0))
         try:
             p._cir_integer_p = hit
