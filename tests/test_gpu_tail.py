@@ -384,6 +384,30 @@ def test_launch_shape_hint_never_changes_the_result(p):
     assert head.pool.p._cir_integer_p == (head.pool.p._version, p != 3.0)
 
 
+def test_inference_inside_a_cuda_graph():
+    """The fused tail (a cooperative launch) can be captured and replayed; a head whose exponent has not been read back yet is
+    captured without a device-to-host copy (general launch shape) and replays to the eager result."""
+    torch.manual_seed(17)
+    x = (torch.relu(torch.randn(6, 128, 16, 16)) + 0.01).to(DEV)
+    warm = _head(128, "GeM", p=3.0).to(DEV)
+    with torch.no_grad():
+        warm(x)                                             # library state (attributes, workspace) exists before the capture
+    head = _head(128, "GeM", p=3.0).to(DEV)                 # fresh exponent tensor: no cached hint
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            y = head(x)
+    assert not hasattr(head.pool.p, "_cir_integer_p")
+    graph.replay()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = head(x)
+    np.testing.assert_allclose(y.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=1e-6)
+    assert head.pool.p._cir_integer_p[1] is True
+
+
 def test_cpu_tensor_is_rejected():
     from cirtorch_b200._lib import CirError
     head = _head(16)
