@@ -2,13 +2,15 @@
 //
 // Replaces cirtorch/modules/pools.py:37-38, normalizations.py:15-16 and
 // heads/global_head.py:52-67 (seven eager PyTorch ops, three full passes over the map)
-// with ONE cooperative launch of one 512-thread CTA per SM:
-//   phase A  the HBM stream.  Warp 15 is a producer: one thread feeds a ring of 16 KB shared-memory slots with
-//            cp.async.bulk (TMA bulk copies of whole (n, c) rows, L2 evict-first) completing on mbarriers; warps 0..14
-//            consume rows from shared memory (clamp, x^p, sum / max; warp-shuffle reduce) and finish 32 rows at a time
+// with ONE cooperative launch of one CTA per SM, in one of two shapes (TAIL_THREADS_LIGHT / _HEAVY: 512 threads for cheap rows,
+// 640 for a non-integer exponent):
+//   phase A  the HBM stream.  The last warp is a producer: one thread feeds a ring of 16 KB shared-memory slots with
+//            cp.async.bulk (TMA bulk copies of whole (n, c) rows, L2 evict-first) completing on mbarriers; the other 15 / 19
+//            warps consume rows from shared memory (clamp, x^p, sum / max; warp-shuffle reduce) and finish 32 rows at a time
 //            (mean^(1/p)).  The bytes in flight are the ring, not registers.  The consumer loop is instantiated per
 //            exponent class (p = 1, 2, 3, 4, general, max, mean), so its body is the inlined arithmetic; the (image,
-//            channel) of a row is tracked incrementally.  Between rows the 480 consumer lanes convert this CTA's W tile
+//            channel) of a row is tracked incrementally; with a non-integer exponent a slot is handed back as soon as the
+//            row sits in registers.  Between rows the consumer lanes convert this CTA's W tile
 //            (128 output dims x 256 k, fp32, read from HBM once) into bf16 hi / lo UMMA tiles in shared memory (128 KB).
 //            Rows that TMA cannot move (H*W % 4 != 0, > 16 KB, unaligned) take a direct-load path.
 //            Phase A stores the pooled vectors already split into bf16 hi + lo parts (and, on request, as fp32 for the
