@@ -34,7 +34,7 @@ import torch
 
 B, C, H, W, DOUT = 64, 2048, 32, 32, 2048
 TAIL_BYTES = B * C * H * W * 4 + DOUT * C * 4 + DOUT * 4 + B * DOUT * 4          # 554,180,608
-TAIL_NCU_TRAFFIC = 553_867_776 + 4_335_104      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r2_tail_p3.txt)
+TAIL_NCU_TRAFFIC = 553_788_672 + 3_611_392      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r2_tail_p3.txt)
 DB_N, DB_D, TOPK = 1_000_000, 2048, 100
 WORKLOAD = "fused tail: batch 64x2048x32x32 fp32 maps -> GeM(p=3)+L2N+whiten 2048->2048+L2N"
 METRIC = "descriptors/s (GeM+whiten tail) & queries/s vs 1M×2048 DB at 1/2/4/8 B200, %roofline"
